@@ -1,0 +1,155 @@
+"""ctypes view of the C ABI in include/dpgicp.h (types + loader).
+
+The structures mirror ``dpgicp_params`` / ``dpgicp_result`` field for field; the loader binds the
+in-tree ``libdpgicp.so`` built by ``__graft_entry__.build()`` and raises if it is missing — there
+is no CPU fallback in the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# ---- constants (include/dpgicp.h) -----------------------------------------------------------------
+ABI_VERSION = 1
+METRIC_POINT_TO_POINT, METRIC_POINT_TO_LINE = 0, 1
+SEARCH_BRUTE, SEARCH_PRUNED = 0, 1
+COV_REFERENCE_LIVE, COV_CENSI_INDEXPAIR, COV_CENSI_CORR = 0, 1, 2
+STOP_MASK = 0xFF
+STOP_NONE, STOP_ITERATIONS, STOP_TRANSFORM, STOP_ABS_MSE, STOP_NO_CORRESPONDENCES = 0, 1, 2, 3, 4
+FLAG_CONVERGED, FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT = 0x100, 0x200, 0x400
+MAX_ABS_COORD = 1000.0
+MAX_POINTS = 8192
+
+ERRORS = {0: "OK", -1: "E_INVALID", -2: "E_NODEVICE", -3: "E_CUDA", -4: "E_NOMEM", -5: "E_RANGE",
+          -6: "E_STATE", -7: "E_TOOBIG"}
+
+
+class Params(C.Structure):
+    """``dpgicp_params``; defaults are the reference's parameters.h values."""
+    _fields_ = [
+        ("max_iterations", C.c_int32),
+        ("use_reciprocal", C.c_int32),
+        ("ransac_iterations", C.c_int32),
+        ("downsample_divisor", C.c_int32),
+        ("metric", C.c_int32),
+        ("search", C.c_int32),
+        ("cov_mode", C.c_int32),
+        ("cov_cap", C.c_int32),
+        ("transformation_epsilon", C.c_double),
+        ("max_correspondence_distance", C.c_double),
+        ("cov_sensor_variance", C.c_double),
+        ("laser_x_variance", C.c_float),
+        ("laser_y_variance", C.c_float),
+        ("laser_theta_variance", C.c_float),
+        ("reserved0", C.c_int32),
+    ]
+
+    @classmethod
+    def defaults(cls, **overrides) -> "Params":
+        """parameters.h:146,159,173,191,201,374,385,396,402; cov_func_point_to_point.h:307,554."""
+        p = cls(max_iterations=500, use_reciprocal=1, ransac_iterations=50, downsample_divisor=5,
+                metric=METRIC_POINT_TO_POINT, search=SEARCH_PRUNED, cov_mode=COV_REFERENCE_LIVE,
+                cov_cap=200, transformation_epsilon=5e-9, max_correspondence_distance=0.6,
+                cov_sensor_variance=0.01, laser_x_variance=0.5, laser_y_variance=0.5,
+                laser_theta_variance=0.3, reserved0=0)
+        for k, v in overrides.items():
+            if not hasattr(p, k):
+                raise AttributeError(f"dpgicp_params has no field {k!r}")
+            setattr(p, k, v)
+        return p
+
+    def copy(self, **overrides) -> "Params":
+        q = Params.from_buffer_copy(bytes(self))
+        for k, v in overrides.items():
+            if not hasattr(q, k):
+                raise AttributeError(f"dpgicp_params has no field {k!r}")
+            setattr(q, k, v)
+        return q
+
+
+class Result(C.Structure):
+    """``dpgicp_result`` (112 bytes)."""
+    _fields_ = [
+        ("tx", C.c_float), ("ty", C.c_float), ("theta", C.c_float),
+        ("rot_c", C.c_float), ("rot_s", C.c_float),
+        ("iterations", C.c_int32), ("status", C.c_uint32), ("n_correspondences", C.c_int32),
+        ("mse", C.c_double),
+        ("cov", C.c_double * 9),
+    ]
+
+
+RESULT_DTYPE = np.dtype([
+    ("tx", "<f4"), ("ty", "<f4"), ("theta", "<f4"), ("rot_c", "<f4"), ("rot_s", "<f4"),
+    ("iterations", "<i4"), ("status", "<u4"), ("n_correspondences", "<i4"),
+    ("mse", "<f8"), ("cov", "<f8", (9,)),
+], align=True)
+
+assert C.sizeof(Result) == 112 and RESULT_DTYPE.itemsize == 112
+assert C.sizeof(Params) == 72
+
+EXPORTS = [
+    "dpgicp_abi_version", "dpgicp_default_params", "dpgicp_create", "dpgicp_destroy",
+    "dpgicp_last_error", "dpgicp_set_stream", "dpgicp_synchronize", "dpgicp_upload_scans",
+    "dpgicp_upload_ranges", "dpgicp_scan_count", "dpgicp_download_scan", "dpgicp_submit_pairs",
+    "dpgicp_set_pairs", "dpgicp_run", "dpgicp_fetch_results", "dpgicp_results_device_ptr",
+    "dpgicp_last_run_counters", "dpgicp_single_pair", "dpgicp_cov", "dpgicp_correspondences",
+    "dpgicp_enumerate_pairs", "dpgicp_relative_guess",
+]
+
+_lib = None
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libdpgicp.so")
+
+
+def load_library() -> C.CDLL:
+    """Bind libdpgicp.so.  Raises (never falls back) when the CUDA extension is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build the CUDA back end first (python -c 'import __graft_entry__ as g; "
+            "g.build()' or make -C dpg_slam_b200/csrc). dpg_slam_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    PP, PR = C.POINTER(Params), C.POINTER(Result)
+    sig = {
+        "dpgicp_abi_version": (C.c_int, []),
+        "dpgicp_default_params": (C.c_int, [PP]),
+        "dpgicp_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "dpgicp_destroy": (None, [vp]),
+        "dpgicp_last_error": (C.c_char_p, [vp]),
+        "dpgicp_set_stream": (C.c_int, [vp, vp]),
+        "dpgicp_synchronize": (C.c_int, [vp]),
+        "dpgicp_upload_scans": (C.c_int, [vp, vp, sz, vp, i32]),
+        "dpgicp_upload_ranges": (C.c_int, [vp, vp, i32, i32] + [C.c_float] * 6),
+        "dpgicp_scan_count": (C.c_int, [vp]),
+        "dpgicp_download_scan": (C.c_int, [vp, i32, vp, C.POINTER(i32)]),
+        "dpgicp_submit_pairs": (C.c_int, [vp, vp, vp, vp, i64, PP, vp]),
+        "dpgicp_set_pairs": (C.c_int, [vp, vp, vp, vp, i64]),
+        "dpgicp_run": (C.c_int, [vp, PP]),
+        "dpgicp_fetch_results": (C.c_int, [vp, vp, i64]),
+        "dpgicp_results_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "dpgicp_last_run_counters": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
+        "dpgicp_single_pair": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, PR]),
+        "dpgicp_cov": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, vp, C.POINTER(C.c_uint32)]),
+        "dpgicp_correspondences": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, vp, vp]),
+        "dpgicp_relative_guess": (C.c_int, [vp, vp, vp]),
+        "dpgicp_enumerate_pairs": (C.c_int, [vp, vp, vp, i32, C.c_float, C.c_float, vp, vp,
+                                              C.POINTER(i64)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dpgicp_abi_version() != ABI_VERSION:
+        raise RuntimeError("libdpgicp.so ABI version mismatch")
+    _lib = lib
+    return lib

@@ -1,0 +1,651 @@
+/*
+ * dpgicp_abi.cu — host side of the C ABI declared in include/dpgicp.h.
+ *
+ * Thin by design: argument validation, host<->device copies, kernel launches.  All arithmetic of
+ * the path runs in the sm_100a kernels of dpgicp_kernels.cuh; there is no CPU implementation
+ * behind these entry points (dpgicp_create fails without a CUDA device).
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dpgicp.h"
+#include "dpgicp_kernels.cuh"
+
+using namespace dpg;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct Store {                 /* padded rows + counts on the device, counts mirrored on the host */
+  DevBuf rows, count;
+  int32_t pitch = 0, n_scans = 0, max_count = 0;
+  std::vector<int32_t> h_count;
+};
+
+struct Batch {
+  DevBuf tasks, results;
+  PairTask *h_tasks = nullptr;   /* pinned */
+  size_t h_tasks_cap = 0;
+  int64_t n_pairs = 0;
+};
+
+}  // namespace
+
+struct dpgicp_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  Store store, scratch_store;
+  Batch batch, scratch_batch;
+  DevBuf stage, offsets, misc, corr;
+  unsigned long long *d_queue = nullptr;     /* [0] queue head, [8..15] counters */
+  int *d_bad = nullptr;
+  int force_warps = 0;
+  int force_ctas_per_sm = 0;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(dpgicp_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      return fail(ctx, e__ == cudaErrorMemoryAllocation ? DPGICP_E_NOMEM : DPGICP_E_CUDA,         \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                           \
+    }                                                                                             \
+  } while (0)
+
+int reserve(dpgicp_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return DPGICP_OK;
+  if (b.p) { CU_TRY(ctx, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+  size_t want = std::max(bytes, (size_t)256);
+  CU_TRY(ctx, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return DPGICP_OK;
+}
+
+void release(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.cap = 0;
+}
+
+int check_params(dpgicp_ctx *ctx, const dpgicp_params *p) {
+  if (!p) return fail(ctx, DPGICP_E_INVALID, "params is NULL");
+  if (p->max_iterations < 1) return fail(ctx, DPGICP_E_INVALID, "max_iterations must be >= 1");
+  if (p->downsample_divisor < 1) return fail(ctx, DPGICP_E_INVALID, "downsample_divisor must be >= 1");
+  if (!(p->max_correspondence_distance > 0.0) || !std::isfinite(p->max_correspondence_distance))
+    return fail(ctx, DPGICP_E_INVALID, "max_correspondence_distance must be positive and finite");
+  if (!(p->transformation_epsilon >= 0.0)) return fail(ctx, DPGICP_E_INVALID, "transformation_epsilon must be >= 0");
+  if (p->metric != DPGICP_METRIC_POINT_TO_POINT)
+    return fail(ctx, DPGICP_E_INVALID, "metric: only DPGICP_METRIC_POINT_TO_POINT is implemented");
+  if (p->search != DPGICP_SEARCH_BRUTE && p->search != DPGICP_SEARCH_PRUNED)
+    return fail(ctx, DPGICP_E_INVALID, "search must be DPGICP_SEARCH_BRUTE or DPGICP_SEARCH_PRUNED");
+  if (p->cov_mode < DPGICP_COV_REFERENCE_LIVE || p->cov_mode > DPGICP_COV_CENSI_CORR)
+    return fail(ctx, DPGICP_E_INVALID, "cov_mode out of range");
+  if (p->cov_cap < 0) return fail(ctx, DPGICP_E_INVALID, "cov_cap must be >= 0");
+  return DPGICP_OK;
+}
+
+/* largest binary32 <= max_correspondence_distance^2 (binary64): same predicate as PCL's
+ * `float_distance > double_threshold` */
+float gate_threshold(const dpgicp_params *p) {
+  const double d = p->max_correspondence_distance * p->max_correspondence_distance;
+  float f = (float)d;
+  if ((double)f > d) f = std::nextafterf(f, -INFINITY);
+  return f;
+}
+
+template <int WARPS, bool PRUNED>
+int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t n_pairs) {
+  auto kern = icp_pairs_kernel<WARPS, PRUNED>;
+  CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+  if (per_sm < 1) return fail(ctx, DPGICP_E_TOOBIG, "scan too large for one CTA's shared memory");
+  if (ctx->force_ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->force_ctas_per_sm);
+  /* persistent grid: a whole number of resident CTAs per SM, never more CTAs than pairs */
+  int64_t grid = (int64_t)ctx->sm_count * per_sm;
+  if (grid > n_pairs) grid = n_pairs;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(kp);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  return DPGICP_OK;
+}
+
+template <bool PRUNED>
+int launch_icp_w(dpgicp_ctx *ctx, int warps, const KernelParams &kp, size_t smem, int64_t n) {
+  switch (warps) {
+    case 1: return launch_icp_t<1, PRUNED>(ctx, kp, smem, n);
+    case 2: return launch_icp_t<2, PRUNED>(ctx, kp, smem, n);
+    case 4: return launch_icp_t<4, PRUNED>(ctx, kp, smem, n);
+    case 8: return launch_icp_t<8, PRUNED>(ctx, kp, smem, n);
+    default: return launch_icp_t<16, PRUNED>(ctx, kp, smem, n);
+  }
+}
+
+int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_params *p, int32_t *corr_out,
+               float *corr_d2) {
+  const int div = p->downsample_divisor;
+  int n_max = (st.max_count + div - 1) / div;
+  int n_cap = ((std::max(n_max, 1) + kGroup - 1) / kGroup) * kGroup;
+  if (n_cap > DPGICP_MAX_POINTS) return fail(ctx, DPGICP_E_TOOBIG, "scan exceeds DPGICP_MAX_POINTS");
+  KernelParams kp;
+  std::memset(&kp, 0, sizeof(kp));
+  kp.store.pts = (const float2 *)st.rows.p;
+  kp.store.count = (const int32_t *)st.count.p;
+  kp.store.pitch = st.pitch;
+  kp.store.n_scans = st.n_scans;
+  kp.tasks = (const PairTask *)b.tasks.p;
+  kp.results = (dpgicp_result *)b.results.p;
+  kp.queue = ctx->d_queue;
+  kp.counters = ctx->d_queue + 8;
+  kp.n_pairs = b.n_pairs;
+  kp.n_cap = n_cap;
+  kp.max_iterations = p->max_iterations;
+  kp.use_reciprocal = p->use_reciprocal;
+  kp.divisor = div;
+  kp.metric = p->metric;
+  kp.cov_mode = p->cov_mode;
+  kp.cov_cap = p->cov_cap;
+  kp.gate = gate_threshold(p);
+  kp.eps = p->transformation_epsilon;
+  kp.rot_thr = 1.0 - p->transformation_epsilon;
+  kp.sensor_var = p->cov_sensor_variance;
+  kp.live[0] = p->laser_x_variance; kp.live[1] = p->laser_y_variance; kp.live[2] = p->laser_theta_variance;
+  kp.corr_out = corr_out;
+  kp.corr_d2_out = corr_d2;
+  const size_t smem = smem_bytes(n_cap);
+  int warps = ctx->force_warps;
+  if (warps <= 0) warps = n_cap <= 512 ? 2 : (n_cap <= 2048 ? 4 : 8);
+  CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  if (p->search == DPGICP_SEARCH_PRUNED) return launch_icp_w<true>(ctx, warps, kp, smem, b.n_pairs);
+  return launch_icp_w<false>(ctx, warps, kp, smem, b.n_pairs);
+}
+
+int finish_store(dpgicp_ctx *ctx, Store &st, int n_scans) {
+  /* counts back to the host (sizing of shared memory, argument validation) + range flag */
+  st.h_count.resize((size_t)n_scans);
+  int bad = 0;
+  CU_TRY(ctx, cudaMemcpyAsync(st.h_count.data(), st.count.p, sizeof(int32_t) * (size_t)n_scans,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(&bad, ctx->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  st.n_scans = n_scans;
+  st.max_count = 0;
+  for (int32_t c : st.h_count) st.max_count = std::max(st.max_count, c);
+  if (bad) {
+    st.n_scans = 0;
+    return fail(ctx, DPGICP_E_RANGE, "scan store holds a non-finite point or |coordinate| > DPGICP_MAX_ABS_COORD");
+  }
+  return DPGICP_OK;
+}
+
+int upload_scans_into(dpgicp_ctx *ctx, Store &st, const void *points, size_t stride, const int64_t *offsets,
+                      int32_t n_scans) {
+  if (n_scans < 0 || (n_scans > 0 && (!offsets))) return fail(ctx, DPGICP_E_INVALID, "bad scan arguments");
+  if (stride < 8 || (stride % 4) != 0) return fail(ctx, DPGICP_E_INVALID, "stride_bytes must be >= 8 and a multiple of 4");
+  int64_t maxc = 0;
+  for (int k = 0; k < n_scans; ++k) {
+    const int64_t c = offsets[k + 1] - offsets[k];
+    if (c < 0 || offsets[k] < 0) return fail(ctx, DPGICP_E_INVALID, "offsets must be non-negative and non-decreasing");
+    maxc = std::max(maxc, c);
+  }
+  if (maxc > DPGICP_MAX_POINTS) return fail(ctx, DPGICP_E_TOOBIG, "a scan has more than DPGICP_MAX_POINTS points");
+  const int64_t total = n_scans > 0 ? offsets[n_scans] : 0;
+  if (total > 0 && !points) return fail(ctx, DPGICP_E_INVALID, "points is NULL");
+  const int pitch = (int)std::max<int64_t>(2, (maxc + 1) & ~(int64_t)1);
+  int rc;
+  if ((rc = reserve(ctx, st.rows, sizeof(float2) * (size_t)pitch * (size_t)std::max(n_scans, 1)))) return rc;
+  if ((rc = reserve(ctx, st.count, sizeof(int32_t) * (size_t)std::max(n_scans, 1)))) return rc;
+  if ((rc = reserve(ctx, ctx->stage, (size_t)total * stride + 16))) return rc;
+  if ((rc = reserve(ctx, ctx->offsets, sizeof(int64_t) * ((size_t)n_scans + 1)))) return rc;
+  st.pitch = pitch;
+  st.n_scans = 0;
+  CU_TRY(ctx, cudaMemsetAsync(ctx->d_bad, 0, sizeof(int), ctx->stream));
+  if (n_scans == 0) { st.max_count = 0; st.h_count.clear(); return DPGICP_OK; }
+  if (total > 0)
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->stage.p, points, (size_t)total * stride, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->offsets.p, offsets, sizeof(int64_t) * ((size_t)n_scans + 1),
+                              cudaMemcpyHostToDevice, ctx->stream));
+  pack_rows_kernel<<<n_scans, 256, 0, ctx->stream>>>((const unsigned char *)ctx->stage.p, stride,
+                                                     (const long long *)ctx->offsets.p, n_scans, pitch,
+                                                     (float2 *)st.rows.p, (int32_t *)st.count.p, ctx->d_bad);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  return finish_store(ctx, st, n_scans);
+}
+
+int set_pairs_into(dpgicp_ctx *ctx, const Store &st, Batch &b, const int32_t *src, const int32_t *tgt,
+                   const float *guess, const float *T_direct, int64_t n) {
+  if (n < 0 || (n > 0 && (!src || !tgt || (!guess && !T_direct))))
+    return fail(ctx, DPGICP_E_INVALID, "bad pair arguments");
+  if (st.n_scans <= 0 && n > 0) return fail(ctx, DPGICP_E_STATE, "no scans uploaded");
+  if ((size_t)n > b.h_tasks_cap) {
+    if (b.h_tasks) cudaFreeHost(b.h_tasks);
+    b.h_tasks = nullptr; b.h_tasks_cap = 0;
+    CU_TRY(ctx, cudaMallocHost((void **)&b.h_tasks, sizeof(PairTask) * (size_t)n));
+    b.h_tasks_cap = (size_t)n;
+  }
+  for (int64_t k = 0; k < n; ++k) {
+    if (src[k] < 0 || src[k] >= st.n_scans || tgt[k] < 0 || tgt[k] >= st.n_scans)
+      return fail(ctx, DPGICP_E_INVALID, "pair index out of range at pair " + std::to_string(k));
+    PairTask t;
+    t.src = src[k]; t.tgt = tgt[k];
+    if (T_direct) {
+      t.c = T_direct[4 * k]; t.s = T_direct[4 * k + 1]; t.tx = T_direct[4 * k + 2]; t.ty = T_direct[4 * k + 3];
+    } else {
+      /* Matrix4f guess of runIcp (dpg_slam.cc:374-378): cos/sin of the float angle, binary64 libm
+       * rounded to binary32 (computed on the host so device and CPU agree bit for bit) */
+      const float g0 = guess[3 * k], g1 = guess[3 * k + 1], g2 = guess[3 * k + 2];
+      if (!std::isfinite(g0) || !std::isfinite(g1) || !std::isfinite(g2))
+        return fail(ctx, DPGICP_E_RANGE, "non-finite guess at pair " + std::to_string(k));
+      t.c = (float)std::cos((double)g2); t.s = (float)std::sin((double)g2); t.tx = g0; t.ty = g1;
+    }
+    b.h_tasks[k] = t;
+  }
+  int rc;
+  if ((rc = reserve(ctx, b.tasks, sizeof(PairTask) * (size_t)std::max<int64_t>(n, 1)))) return rc;
+  if ((rc = reserve(ctx, b.results, sizeof(dpgicp_result) * (size_t)std::max<int64_t>(n, 1)))) return rc;
+  if (n > 0)
+    CU_TRY(ctx, cudaMemcpyAsync(b.tasks.p, b.h_tasks, sizeof(PairTask) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  b.n_pairs = n;
+  return DPGICP_OK;
+}
+
+/* host repack of an arbitrary-stride cloud into packed float2 */
+void pack_host(const void *pts, int n, size_t stride, std::vector<float> &out) {
+  out.resize((size_t)std::max(n, 0) * 2);
+  const unsigned char *b = (const unsigned char *)pts;
+  for (int k = 0; k < n; ++k) {
+    const float *f = (const float *)(b + (size_t)k * stride);
+    out[2 * k] = f[0]; out[2 * k + 1] = f[1];
+  }
+}
+
+int two_cloud_store(dpgicp_ctx *ctx, const void *a, int na, const void *b, int nb, size_t stride) {
+  if (na < 0 || nb < 0 || (na > 0 && !a) || (nb > 0 && !b)) return fail(ctx, DPGICP_E_INVALID, "bad cloud arguments");
+  if (stride < 8 || (stride % 4) != 0) return fail(ctx, DPGICP_E_INVALID, "stride_bytes must be >= 8 and a multiple of 4");
+  std::vector<float> pa, pb;
+  pack_host(a, na, stride, pa);
+  pack_host(b, nb, stride, pb);
+  pa.insert(pa.end(), pb.begin(), pb.end());
+  const int64_t off[3] = {0, na, (int64_t)na + nb};
+  return upload_scans_into(ctx, ctx->scratch_store, pa.data(), 8, off, 2);
+}
+
+}  // namespace
+
+/* ================================================================================================
+ * exported C ABI
+ * ============================================================================================== */
+extern "C" {
+
+int dpgicp_abi_version(void) { return DPGICP_ABI_VERSION; }
+
+int dpgicp_default_params(dpgicp_params *p) {
+  if (!p) return DPGICP_E_INVALID;
+  std::memset(p, 0, sizeof(*p));
+  p->max_iterations = 500;                  /* parameters.h:146 */
+  p->use_reciprocal = 1;                    /* parameters.h:201 */
+  p->ransac_iterations = 50;                /* parameters.h:191 */
+  p->downsample_divisor = 5;                /* parameters.h:402 */
+  p->metric = DPGICP_METRIC_POINT_TO_POINT;
+  p->search = DPGICP_SEARCH_PRUNED;
+  p->cov_mode = DPGICP_COV_REFERENCE_LIVE;  /* cov.h:572-575 */
+  p->cov_cap = 200;                         /* cov.h:307 */
+  p->transformation_epsilon = 5e-9;         /* parameters.h:159 */
+  p->max_correspondence_distance = 0.6;     /* parameters.h:173 */
+  p->cov_sensor_variance = 0.01;            /* cov.h:554 */
+  p->laser_x_variance = 0.5f;               /* parameters.h:374 */
+  p->laser_y_variance = 0.5f;               /* parameters.h:385 */
+  p->laser_theta_variance = 0.3f;           /* parameters.h:396 */
+  return DPGICP_OK;
+}
+
+int dpgicp_create(int device, dpgicp_ctx **out) {
+  if (!out) return fail(nullptr, DPGICP_E_INVALID, "out_ctx is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(nullptr, DPGICP_E_NODEVICE,
+                std::string("no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                    "); this library has no CPU fallback");
+  if (device < 0 || device >= n) return fail(nullptr, DPGICP_E_NODEVICE, "device ordinal out of range");
+  dpgicp_ctx *ctx = new (std::nothrow) dpgicp_ctx();
+  if (!ctx) return fail(nullptr, DPGICP_E_NOMEM, "out of host memory");
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, DPGICP_E_CUDA, cudaGetErrorString(e));
+  }
+  if (prop.major < 10) {
+    delete ctx;
+    return fail(nullptr, DPGICP_E_NODEVICE, "device is not sm_100 class; this library is built for sm_100a only");
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMalloc((void **)&ctx->d_queue, 16 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc((void **)&ctx->d_bad, sizeof(int))) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, DPGICP_E_CUDA, cudaGetErrorString(e));
+  }
+  if (const char *w = std::getenv("DPGICP_WARPS")) ctx->force_warps = std::atoi(w);
+  if (const char *c = std::getenv("DPGICP_CTAS_PER_SM")) ctx->force_ctas_per_sm = std::atoi(c);
+  *out = ctx;
+  return DPGICP_OK;
+}
+
+void dpgicp_destroy(dpgicp_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (Store *s : {&ctx->store, &ctx->scratch_store}) { release(s->rows); release(s->count); }
+  for (Batch *b : {&ctx->batch, &ctx->scratch_batch}) {
+    release(b->tasks); release(b->results);
+    if (b->h_tasks) cudaFreeHost(b->h_tasks);
+  }
+  release(ctx->stage); release(ctx->offsets); release(ctx->misc); release(ctx->corr);
+  if (ctx->d_queue) cudaFree(ctx->d_queue);
+  if (ctx->d_bad) cudaFree(ctx->d_bad);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *dpgicp_last_error(const dpgicp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dpgicp_set_stream(dpgicp_ctx *ctx, void *stream) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stream) {
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)stream;
+    ctx->own_stream = false;
+  } else if (!ctx->own_stream) {
+    CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return DPGICP_OK;
+}
+
+int dpgicp_synchronize(dpgicp_ctx *ctx) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
+}
+
+int dpgicp_upload_scans(dpgicp_ctx *ctx, const void *points, size_t stride, const int64_t *offsets, int32_t n_scans) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->batch.n_pairs = 0;
+  return upload_scans_into(ctx, ctx->store, points, stride, offsets, n_scans);
+}
+
+int dpgicp_upload_ranges(dpgicp_ctx *ctx, const float *ranges, int32_t n_scans, int32_t n_beams, float angle_min,
+                         float angle_max, float range_max, float lx, float ly, float ltheta) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_scans < 0 || n_beams < 2 || (n_scans > 0 && !ranges)) return fail(ctx, DPGICP_E_INVALID, "bad range-scan arguments");
+  if (n_beams > DPGICP_MAX_POINTS) return fail(ctx, DPGICP_E_TOOBIG, "n_beams exceeds DPGICP_MAX_POINTS");
+  Store &st = ctx->store;
+  ctx->batch.n_pairs = 0;
+  const int pitch = (n_beams + 1) & ~1;
+  int rc;
+  if ((rc = reserve(ctx, st.rows, sizeof(float2) * (size_t)pitch * (size_t)std::max(n_scans, 1)))) return rc;
+  if ((rc = reserve(ctx, st.count, sizeof(int32_t) * (size_t)std::max(n_scans, 1)))) return rc;
+  if ((rc = reserve(ctx, ctx->stage, sizeof(float) * (size_t)n_scans * (size_t)n_beams + 16))) return rc;
+  st.pitch = pitch;
+  st.n_scans = 0;
+  if (n_scans == 0) { st.max_count = 0; st.h_count.clear(); return DPGICP_OK; }
+  CU_TRY(ctx, cudaMemsetAsync(ctx->d_bad, 0, sizeof(int), ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->stage.p, ranges, sizeof(float) * (size_t)n_scans * (size_t)n_beams,
+                              cudaMemcpyHostToDevice, ctx->stream));
+  /* createNode dpg_slam.cc:497: angle_inc = (max - min) / (n - 1.0), stored as float */
+  const float angle_inc = (float)(((double)(float)(angle_max - angle_min)) / ((double)n_beams - 1.0));
+  const float lc = cosf(ltheta), ls = sinf(ltheta);       /* Eigen::Rotation2Df(ltheta), host libm */
+  const int threads = 128, warps_per_block = threads / 32;
+  const int blocks = (n_scans + warps_per_block - 1) / warps_per_block;
+  ranges_to_rows_kernel<<<blocks, threads, 0, ctx->stream>>>((const float *)ctx->stage.p, n_scans, n_beams, angle_min,
+                                                            angle_inc, range_max, lx, ly, lc, ls, pitch,
+                                                            (float2 *)st.rows.p, (int32_t *)st.count.p, ctx->d_bad);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  return finish_store(ctx, st, n_scans);
+}
+
+int dpgicp_scan_count(const dpgicp_ctx *ctx) { return ctx ? ctx->store.n_scans : DPGICP_E_INVALID; }
+
+int dpgicp_download_scan(dpgicp_ctx *ctx, int32_t scan, float *xy, int32_t *n_points) {
+  if (!ctx || !n_points) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const Store &st = ctx->store;
+  if (scan < 0 || scan >= st.n_scans) return fail(ctx, DPGICP_E_INVALID, "scan index out of range");
+  const int n = st.h_count[(size_t)scan];
+  if (*n_points < n || (n > 0 && !xy)) { *n_points = n; return fail(ctx, DPGICP_E_TOOBIG, "output capacity too small"); }
+  *n_points = n;
+  if (n > 0) {
+    CU_TRY(ctx, cudaMemcpyAsync(xy, (const float2 *)st.rows.p + (size_t)scan * st.pitch, sizeof(float2) * (size_t)n,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return DPGICP_OK;
+}
+
+int dpgicp_set_pairs(dpgicp_ctx *ctx, const int32_t *src, const int32_t *tgt, const float *guess, int64_t n) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  return set_pairs_into(ctx, ctx->store, ctx->batch, src, tgt, guess, nullptr, n);
+}
+
+int dpgicp_run(dpgicp_ctx *ctx, const dpgicp_params *params) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = check_params(ctx, params);
+  if (rc) return rc;
+  if (ctx->store.n_scans <= 0) return fail(ctx, DPGICP_E_STATE, "no scans uploaded");
+  if (ctx->batch.n_pairs <= 0) return ctx->batch.n_pairs == 0 ? DPGICP_OK : DPGICP_E_STATE;
+  return launch_icp(ctx, ctx->store, ctx->batch, params, nullptr, nullptr);
+}
+
+int dpgicp_fetch_results(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n < 0 || n > ctx->batch.n_pairs || (n > 0 && !out)) return fail(ctx, DPGICP_E_INVALID, "bad fetch arguments");
+  if (n > 0)
+    CU_TRY(ctx, cudaMemcpyAsync(out, ctx->batch.results.p, sizeof(dpgicp_result) * (size_t)n, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
+}
+
+int dpgicp_results_device_ptr(dpgicp_ctx *ctx, void **out_ptr, int64_t *out_n) {
+  if (!ctx || !out_ptr || !out_n) return DPGICP_E_INVALID;
+  *out_ptr = ctx->batch.results.p;
+  *out_n = ctx->batch.n_pairs;
+  return DPGICP_OK;
+}
+
+int dpgicp_last_run_counters(dpgicp_ctx *ctx, uint64_t counters[8]) {
+  if (!ctx || !counters) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  unsigned long long h[8];
+  CU_TRY(ctx, cudaMemcpyAsync(h, ctx->d_queue + 8, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 8; ++k) counters[k] = h[k];
+  counters[4] = ctx->launches;
+  return DPGICP_OK;
+}
+
+int dpgicp_submit_pairs(dpgicp_ctx *ctx, const int32_t *src, const int32_t *tgt, const float *guess, int64_t n,
+                        const dpgicp_params *params, dpgicp_result *out) {
+  int rc;
+  if ((rc = dpgicp_set_pairs(ctx, src, tgt, guess, n))) return rc;
+  if ((rc = dpgicp_run(ctx, params))) return rc;
+  return dpgicp_fetch_results(ctx, out, n);
+}
+
+int dpgicp_relative_guess(const float p1[3], const float p2[3], float guess[3]) {
+  if (!p1 || !p2 || !guess) return DPGICP_E_INVALID;
+  /* translate, rotate by Rotation2Df(-theta_1) (cosf/sinf of the float angle), AngleMod */
+  const float tx = p2[0] - p1[0], ty = p2[1] - p1[1];
+  const float ang = -p1[2];
+  const float c = cosf(ang), s = sinf(ang), ms = -s;
+  guess[0] = (c * tx) + (ms * ty);
+  guess[1] = (s * tx) + (c * ty);
+  double d = (double)(float)(p2[2] - p1[2]);
+  d -= (M_PI * 2.0) * rint(d / (M_PI * 2.0));
+  guess[2] = (float)d;
+  return DPGICP_OK;
+}
+
+int dpgicp_single_pair(dpgicp_ctx *ctx, const void *source, int32_t n_source, const void *target, int32_t n_target,
+                       size_t stride, const float guess[3], const dpgicp_params *params, dpgicp_result *out) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = check_params(ctx, params);
+  if (rc) return rc;
+  if (!guess || !out) return fail(ctx, DPGICP_E_INVALID, "guess/out is NULL");
+  if ((rc = two_cloud_store(ctx, source, n_source, target, n_target, stride))) return rc;
+  const int32_t s = 0, t = 1;
+  if ((rc = set_pairs_into(ctx, ctx->scratch_store, ctx->scratch_batch, &s, &t, guess, nullptr, 1))) return rc;
+  if ((rc = launch_icp(ctx, ctx->scratch_store, ctx->scratch_batch, params, nullptr, nullptr))) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(out, ctx->scratch_batch.results.p, sizeof(dpgicp_result), cudaMemcpyDeviceToHost,
+                              ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
+}
+
+int dpgicp_correspondences(dpgicp_ctx *ctx, const void *source, int32_t n_source, const void *target,
+                           int32_t n_target, size_t stride, const float T[4], const dpgicp_params *params,
+                           int32_t *corr_tgt, float *corr_d2) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = check_params(ctx, params);
+  if (rc) return rc;
+  if (!T || (n_source > 0 && (!corr_tgt || !corr_d2))) return fail(ctx, DPGICP_E_INVALID, "T/corr outputs NULL");
+  if ((rc = two_cloud_store(ctx, source, n_source, target, n_target, stride))) return rc;
+  const int32_t s = 0, t = 1;
+  if ((rc = set_pairs_into(ctx, ctx->scratch_store, ctx->scratch_batch, &s, &t, nullptr, T, 1))) return rc;
+  const size_t n = (size_t)std::max(n_source, 1);
+  if ((rc = reserve(ctx, ctx->corr, n * 8))) return rc;
+  dpgicp_params p = *params;
+  p.downsample_divisor = 1;          /* the clouds given here are the ICP clouds */
+  int32_t *d_corr = (int32_t *)ctx->corr.p;
+  float *d_d2 = (float *)((char *)ctx->corr.p + n * 4);
+  if ((rc = launch_icp(ctx, ctx->scratch_store, ctx->scratch_batch, &p, d_corr, d_d2))) return rc;
+  if (n_source > 0) {
+    CU_TRY(ctx, cudaMemcpyAsync(corr_tgt, d_corr, sizeof(int32_t) * (size_t)n_source, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(corr_d2, d_d2, sizeof(float) * (size_t)n_source, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
+}
+
+int dpgicp_cov(dpgicp_ctx *ctx, const void *data_pi, int32_t n_data, const void *model_qi, int32_t n_model,
+               size_t stride, const float Tm[16], const dpgicp_params *params, double cov_out[9], uint32_t *status_out) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = check_params(ctx, params);
+  if (rc) return rc;
+  if (!Tm || !cov_out) return fail(ctx, DPGICP_E_INVALID, "transform/cov_out is NULL");
+  if (params->cov_mode == DPGICP_COV_CENSI_CORR)
+    return fail(ctx, DPGICP_E_INVALID, "dpgicp_cov pairs the clouds by index (LIVE or CENSI_INDEXPAIR); "
+                                       "CENSI_CORR needs the ICP run (dpgicp_single_pair / submit_pairs)");
+  if ((rc = two_cloud_store(ctx, data_pi, n_data, model_qi, n_model, stride))) return rc;
+  const Store &st = ctx->scratch_store;
+  CovItem it;
+  it.p = (const float2 *)st.rows.p;
+  it.q = (const float2 *)st.rows.p + st.pitch;
+  it.n_p = n_data; it.n_q = n_model;
+  it.c = Tm[0];  it.s = Tm[1];      /* column-major Matrix4f: T(0,0) = m[0], T(1,0) = m[1] */
+  it.tx = Tm[12]; it.ty = Tm[13];   /* T(0,3) = m[12], T(1,3) = m[13]                      */
+  if ((rc = reserve(ctx, ctx->misc, sizeof(CovItem) + 9 * sizeof(double) + 16))) return rc;
+  char *base = (char *)ctx->misc.p;
+  double *d_cov = (double *)base;
+  uint32_t *d_status = (uint32_t *)(base + 9 * sizeof(double));
+  CovItem *d_item = (CovItem *)(base + 9 * sizeof(double) + 16);
+  CU_TRY(ctx, cudaMemcpyAsync(d_item, &it, sizeof(it), cudaMemcpyHostToDevice, ctx->stream));
+  cov_indexpair_kernel<8><<<1, 256, 0, ctx->stream>>>(d_item, 1, params->cov_mode, params->cov_cap,
+                                                      params->cov_sensor_variance, params->laser_x_variance,
+                                                      params->laser_y_variance, params->laser_theta_variance, d_cov,
+                                                      d_status);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  uint32_t status = 0;
+  CU_TRY(ctx, cudaMemcpyAsync(cov_out, d_cov, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(&status, d_status, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (status_out) *status_out = status;
+  return DPGICP_OK;
+}
+
+int dpgicp_enumerate_pairs(dpgicp_ctx *ctx, const float *node_xy, const int32_t *node_pass, int32_t n_nodes,
+                           float r_same, float r_other, int32_t *src, int32_t *tgt, int64_t *n_pairs) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_nodes < 0 || !n_pairs || (n_nodes > 0 && (!node_xy || !node_pass)))
+    return fail(ctx, DPGICP_E_INVALID, "bad node arguments");
+  const int64_t capacity = *n_pairs;
+  *n_pairs = 0;
+  if (n_nodes < 2) return DPGICP_OK;
+  const size_t n = (size_t)n_nodes;
+  int rc;
+  if ((rc = reserve(ctx, ctx->misc, n * (8 + 4 + 8) + 64))) return rc;
+  char *base = (char *)ctx->misc.p;
+  float2 *d_xy = (float2 *)base;
+  unsigned long long *d_cnt = (unsigned long long *)(base + n * 8);
+  int32_t *d_pass = (int32_t *)(base + n * 16);
+  CU_TRY(ctx, cudaMemcpyAsync(d_xy, node_xy, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(d_pass, node_pass, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = 128, blocks = (n_nodes + threads - 1) / threads;
+  enumerate_count_kernel<<<blocks, threads, 0, ctx->stream>>>(d_xy, d_pass, n_nodes, r_same, r_other, d_cnt);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  std::vector<unsigned long long> cnt(n);
+  CU_TRY(ctx, cudaMemcpyAsync(cnt.data(), d_cnt, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  unsigned long long total = 0;
+  for (size_t i = 0; i < n; ++i) { const unsigned long long c = cnt[i]; cnt[i] = total; total += c; }
+  *n_pairs = (int64_t)total;
+  if ((int64_t)total > capacity || (total > 0 && (!src || !tgt)))
+    return fail(ctx, DPGICP_E_TOOBIG, "pair capacity too small; required count returned in *n_pairs");
+  if (total == 0) return DPGICP_OK;
+  if ((rc = reserve(ctx, ctx->stage, (size_t)total * 8 + 16))) return rc;
+  int32_t *d_src = (int32_t *)ctx->stage.p, *d_tgt = d_src + total;
+  CU_TRY(ctx, cudaMemcpyAsync(d_cnt, cnt.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  enumerate_fill_kernel<<<blocks, threads, 0, ctx->stream>>>(d_xy, d_pass, n_nodes, r_same, r_other, d_cnt, d_src, d_tgt);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaMemcpyAsync(src, d_src, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(tgt, d_tgt, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,232 @@
+"""Host-side mirror of the reference's scan-matching interface on top of the C ABI.
+
+``ScanMatcher`` wraps one ``dpgicp_ctx`` (one GPU).  Method names follow the reference:
+
+* :meth:`ScanMatcher.run_icp`            <-> ``DpgSLAM::runIcp``          (src/dpg_slam/dpg_slam.cc:362-446)
+* :meth:`ScanMatcher.calculate_icp_cov`  <-> ``calculate_ICP_COV``        (src/icp_cov/cov_func_point_to_point.h:24)
+* :meth:`ScanMatcher.submit_pairs`       <-> the loops that call runIcp   (dpg_slam.cc:79-107, 255-300)
+* :meth:`ScanMatcher.enumerate_pairs`    <-> reoptimize's distance gate   (dpg_slam.cc:91-98)
+* :func:`relative_guess`                 <-> ``math_utils::inverseTransformPoint`` (math_utils.cc:20-34)
+
+Every compute call goes through ``libdpgicp.so``; a missing library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _abi
+from ._abi import Params, Result, RESULT_DTYPE
+
+
+class DpgIcpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dpgicp error {code} ({_abi.ERRORS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+def relative_guess(pose1, pose2) -> np.ndarray:
+    """Pose of node_2 in node_1's frame as runIcp builds it (dpg_slam.cc:364-370,
+    math_utils::inverseTransformPoint + AngleMod in float arithmetic).  pose = (x, y, theta)."""
+    a = np.ascontiguousarray(pose1, np.float32)
+    b = np.ascontiguousarray(pose2, np.float32)
+    g = np.zeros(3, np.float32)
+    rc = _abi.load_library().dpgicp_relative_guess(a.ctypes.data, b.ctypes.data, g.ctypes.data)
+    if rc != 0:
+        raise DpgIcpError(rc, "dpgicp_relative_guess")
+    return g
+
+
+def _pts(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.float32)
+    if a.ndim != 2 or a.shape[1] not in (2, 4):
+        raise ValueError("point clouds are (n, 2) packed xy or (n, 4) PointXYZ-layout float32 arrays")
+    return a
+
+
+class ScanMatcher:
+    """One GPU's scan-matching context (device scan store + pair batch + kernels)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _abi.load_library()
+        h = C.c_void_p()
+        rc = self._lib.dpgicp_create(device, C.byref(h))
+        if rc != 0:
+            raise DpgIcpError(rc, (self._lib.dpgicp_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise DpgIcpError(rc, (self._lib.dpgicp_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dpgicp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream_handle: Optional[int]):
+        """Run on an existing CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        self._check(self._lib.dpgicp_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)))
+
+    def synchronize(self):
+        self._check(self._lib.dpgicp_synchronize(self._h))
+
+    # ---- scan store ---------------------------------------------------------------------------------
+    def upload_scans(self, points: np.ndarray, offsets: np.ndarray):
+        """CSR scan store: scan k = points[offsets[k]:offsets[k+1]] ((n,2) or (n,4) float32)."""
+        pts = _pts(points) if len(points) else np.zeros((0, 2), np.float32)
+        off = np.ascontiguousarray(offsets, np.int64)
+        self._check(self._lib.dpgicp_upload_scans(self._h, pts.ctypes.data, pts.shape[1] * 4, off.ctypes.data,
+                                                  off.shape[0] - 1))
+
+    def upload_ranges(self, ranges: np.ndarray, scanner):
+        """Raw range scans (n_scans, n_beams), converted on the device (createNode +
+        getCachedPointCloudFromNode)."""
+        r = np.ascontiguousarray(ranges, np.float32)
+        self._check(self._lib.dpgicp_upload_ranges(self._h, r.ctypes.data, r.shape[0], r.shape[1],
+                                                   scanner.angle_min, scanner.angle_max, scanner.range_max,
+                                                   scanner.laser_x, scanner.laser_y, scanner.laser_theta))
+
+    def upload_ranges_ptr(self, host_ptr: int, n_scans: int, n_beams: int, scanner):
+        """Same, from a raw (e.g. pinned) host pointer."""
+        self._check(self._lib.dpgicp_upload_ranges(self._h, C.c_void_p(host_ptr), n_scans, n_beams,
+                                                   scanner.angle_min, scanner.angle_max, scanner.range_max,
+                                                   scanner.laser_x, scanner.laser_y, scanner.laser_theta))
+
+    @property
+    def scan_count(self) -> int:
+        return int(self._lib.dpgicp_scan_count(self._h))
+
+    def download_scan(self, k: int) -> np.ndarray:
+        n = C.c_int32(_abi.MAX_POINTS)
+        buf = np.zeros((_abi.MAX_POINTS, 2), np.float32)
+        self._check(self._lib.dpgicp_download_scan(self._h, k, buf.ctypes.data, C.byref(n)))
+        return np.ascontiguousarray(buf[:n.value])
+
+    def download_store(self) -> Tuple[np.ndarray, np.ndarray]:
+        clouds = [self.download_scan(k) for k in range(self.scan_count)]
+        off = np.zeros(len(clouds) + 1, np.int64)
+        off[1:] = np.cumsum([c.shape[0] for c in clouds])
+        pts = np.concatenate(clouds) if clouds else np.zeros((0, 2), np.float32)
+        return np.ascontiguousarray(pts, np.float32), off
+
+    # ---- batched alignment -----------------------------------------------------------------------------
+    def submit_pairs(self, src_idx, tgt_idx, guess, params: Params) -> np.ndarray:
+        """Align every (source=node_2, target=node_1) pair; returns a RESULT_DTYPE record array."""
+        s = np.ascontiguousarray(src_idx, np.int32)
+        t = np.ascontiguousarray(tgt_idx, np.int32)
+        g = np.ascontiguousarray(guess, np.float32).reshape(-1, 3)
+        if not (s.shape[0] == t.shape[0] == g.shape[0]):
+            raise ValueError("src_idx, tgt_idx and guess must have the same length")
+        out = np.zeros(s.shape[0], RESULT_DTYPE)
+        self._check(self._lib.dpgicp_submit_pairs(self._h, s.ctypes.data, t.ctypes.data, g.ctypes.data, s.shape[0],
+                                                  C.byref(params), out.ctypes.data))
+        return out
+
+    def set_pairs(self, src_idx, tgt_idx, guess):
+        s = np.ascontiguousarray(src_idx, np.int32)
+        t = np.ascontiguousarray(tgt_idx, np.int32)
+        g = np.ascontiguousarray(guess, np.float32).reshape(-1, 3)
+        self._n_pairs = s.shape[0]
+        self._check(self._lib.dpgicp_set_pairs(self._h, s.ctypes.data, t.ctypes.data, g.ctypes.data, s.shape[0]))
+
+    def run(self, params: Params):
+        """Launch the resident batch asynchronously on the context's stream."""
+        self._check(self._lib.dpgicp_run(self._h, C.byref(params)))
+
+    def fetch_results(self, n: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        n = self._n_pairs if n is None else n
+        if out is None:
+            out = np.zeros(n, RESULT_DTYPE)
+        self._check(self._lib.dpgicp_fetch_results(self._h, out.ctypes.data, n))
+        return out
+
+    def fetch_results_ptr(self, host_ptr: int, n: int):
+        self._check(self._lib.dpgicp_fetch_results(self._h, C.c_void_p(host_ptr), n))
+
+    def results_device_ptr(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self._lib.dpgicp_results_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def last_run_counters(self) -> dict:
+        c = (C.c_uint64 * 8)()
+        self._check(self._lib.dpgicp_last_run_counters(self._h, C.byref(c)))
+        return {"iterations": int(c[0]), "correspondences": int(c[1]), "distance_evals": int(c[2]),
+                "box_tests": int(c[3]), "kernel_launches": int(c[4])}
+
+    # ---- the two reference call shapes ----------------------------------------------------------------
+    def run_icp(self, node_1_cloud, node_2_cloud, guess, params: Optional[Params] = None):
+        """``runIcp(node_1, node_2, icp_results)``: aligns node_2's cloud (source) onto node_1's
+        (target) from ``guess`` = pose of node_2 in node_1's frame (use :func:`relative_guess`).
+        Returns ``(converged, ((tx, ty), theta), cov3x3, record)`` — converged is what
+        ``icp.hasConverged()`` returns (dpg_slam.cc:445)."""
+        p = params or Params.defaults()
+        s, t = _pts(node_2_cloud), _pts(node_1_cloud)
+        if s.shape[1] != t.shape[1]:
+            raise ValueError("both clouds must use the same point layout")
+        g = np.ascontiguousarray(guess, np.float32)
+        res = Result()
+        self._check(self._lib.dpgicp_single_pair(self._h, s.ctypes.data, s.shape[0], t.ctypes.data, t.shape[0],
+                                                 s.shape[1] * 4, g.ctypes.data, C.byref(p), C.byref(res)))
+        converged = bool(res.status & _abi.FLAG_CONVERGED)
+        cov = np.array(res.cov, np.float64).reshape(3, 3)
+        return converged, ((res.tx, res.ty), res.theta), cov, res
+
+    def calculate_icp_cov(self, data_pi, model_qi, transform4x4, params: Optional[Params] = None):
+        """``calculate_ICP_COV(data_pi, model_qi, transform, ICP_COV, sx2, sy2, st2)``; the three
+        variances travel in ``params``.  Returns ``(cov3x3, status)``."""
+        p = params or Params.defaults()
+        a, b = _pts(data_pi), _pts(model_qi)
+        T = np.asarray(transform4x4, np.float32).reshape(4, 4)
+        Tc = np.ascontiguousarray(T.T).reshape(16)          # column-major, as Eigen::Matrix4f stores it
+        cov = np.zeros(9, np.float64)
+        st = C.c_uint32(0)
+        self._check(self._lib.dpgicp_cov(self._h, a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], a.shape[1] * 4,
+                                         Tc.ctypes.data, C.byref(p), cov.ctypes.data, C.byref(st)))
+        return cov.reshape(3, 3), int(st.value)
+
+    # ---- parity hook + callers' gate ---------------------------------------------------------------------
+    def correspondences(self, source_ds, target_ds, T, params: Params):
+        """One correspondence pass at iterate T = (c, s, tx, ty) -> (corr_tgt int32, d2 float32)."""
+        s, t = _pts(source_ds), _pts(target_ds)
+        Tm = np.ascontiguousarray(T, np.float32)
+        corr = np.full(max(s.shape[0], 1), -1, np.int32)
+        d2 = np.zeros(max(s.shape[0], 1), np.float32)
+        self._check(self._lib.dpgicp_correspondences(self._h, s.ctypes.data, s.shape[0], t.ctypes.data, t.shape[0],
+                                                     s.shape[1] * 4, Tm.ctypes.data, C.byref(params),
+                                                     corr.ctypes.data, d2.ctypes.data))
+        return corr[:s.shape[0]], d2[:s.shape[0]]
+
+    def enumerate_pairs(self, node_xy, node_pass, same_pass_radius=5.0, other_pass_radius=2.0):
+        """Pair list of one ``reoptimize()`` in the reference's loop order (parameters.h:212,224)."""
+        xy = np.ascontiguousarray(node_xy, np.float32)
+        ps = np.ascontiguousarray(node_pass, np.int32)
+        n = C.c_int64(0)
+        rc = self._lib.dpgicp_enumerate_pairs(self._h, xy.ctypes.data, ps.ctypes.data, xy.shape[0], same_pass_radius,
+                                              other_pass_radius, None, None, C.byref(n))
+        if rc not in (0, -7):
+            self._check(rc)
+        src = np.zeros(n.value, np.int32)
+        tgt = np.zeros(n.value, np.int32)
+        if n.value:
+            self._check(self._lib.dpgicp_enumerate_pairs(self._h, xy.ctypes.data, ps.ctypes.data, xy.shape[0],
+                                                         same_pass_radius, other_pass_radius, src.ctypes.data,
+                                                         tgt.ctypes.data, C.byref(n)))
+        return src, tgt

@@ -1,0 +1,200 @@
+/*
+ * dpgicp.h — C ABI of the B200 scan-matching back end (batched 2D ICP + Censi covariance).
+ *
+ * This is the drop-in boundary for ONE path of DPG-SLAM: the inside of
+ *   bool DpgSLAM::runIcp(DpgNode&, DpgNode&, pair<pair<Vector2f,float>,MatrixXd>&)
+ *        (reference: src/dpg_slam/dpg_slam.cc:362-446, decl src/dpg_slam/dpg_slam.h:630)
+ *   void calculate_ICP_COV(Ptr data_pi, Ptr model_qi, Matrix4f&, MatrixXd&, float, float, float)
+ *        (reference: src/icp_cov/cov_func_point_to_point.h:24-585)
+ * plus the batch form the two callers need (dpg_slam.cc:85,101,263,295).
+ *
+ * Plain C, plain-old-data only; no C++/torch/CUDA types cross this boundary.  All functions
+ * return 0 on success and a negative DPGICP_E_* code on failure (never throw); the message of
+ * the last failure on a context is available from dpgicp_last_error().  There is no CPU
+ * fallback: without a CUDA device dpgicp_create() fails with DPGICP_E_NODEVICE.
+ *
+ * Ownership: the caller owns every host buffer; the library owns device buffers inside the
+ * opaque context.  A context is single-owner (one host thread at a time), as the reference's
+ * callers are single-threaded (src/dpg_slam/dpg_slam_main.cc:328).
+ */
+#ifndef DPGICP_H
+#define DPGICP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPGICP_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------- */
+#define DPGICP_OK            0
+#define DPGICP_E_INVALID    -1   /* bad argument (NULL, negative size, index out of range, ...)  */
+#define DPGICP_E_NODEVICE   -2   /* no CUDA device / device ordinal not present                   */
+#define DPGICP_E_CUDA       -3   /* a CUDA runtime call failed (see dpgicp_last_error)            */
+#define DPGICP_E_NOMEM      -4   /* host or device allocation failed                              */
+#define DPGICP_E_RANGE      -5   /* non-finite point or |coordinate| > DPGICP_MAX_ABS_COORD       */
+#define DPGICP_E_STATE      -6   /* call order violated (e.g. run before pairs were set)          */
+#define DPGICP_E_TOOBIG     -7   /* a scan has more points than DPGICP_MAX_POINTS                 */
+
+/* Arithmetic-contract limits (DESIGN.md "arithmetic contract"): coordinates are binary32 metres,
+ * moment sums are exact 64-bit fixed point, which needs these bounds.                           */
+#define DPGICP_MAX_ABS_COORD 1000.0f
+#define DPGICP_MAX_POINTS    8192
+
+/* ---- enumerations ------------------------------------------------------------------------ */
+/* error metric minimised by each ICP step */
+#define DPGICP_METRIC_POINT_TO_POINT 0   /* what the reference runs (PCL ICP, dpg_slam.cc:387)   */
+#define DPGICP_METRIC_POINT_TO_LINE  1   /* north-star extension; no reference counterpart       */
+
+/* nearest-neighbour search strategy; both are exact and give identical correspondences */
+#define DPGICP_SEARCH_BRUTE   0
+#define DPGICP_SEARCH_PRUNED  1          /* beam-order block bounding boxes + seeded bound       */
+
+/* what is written to result.cov (SURVEY.md §8a "covariance modes") */
+#define DPGICP_COV_REFERENCE_LIVE  0     /* diag(sx2, sy2, st2): cov_func_point_to_point.h:572-575 */
+#define DPGICP_COV_CENSI_INDEXPAIR 1     /* intended formula, clouds paired by index as dpg_slam.cc:430 */
+#define DPGICP_COV_CENSI_CORR      2     /* intended formula on the final ICP correspondences    */
+
+/* result.status: low byte = stop reason, higher bits = flags */
+#define DPGICP_STOP_MASK              0xffu
+#define DPGICP_STOP_NONE              0u   /* never ran                                          */
+#define DPGICP_STOP_ITERATIONS        1u   /* max_iterations reached (PCL reports converged)     */
+#define DPGICP_STOP_TRANSFORM         2u   /* step below transformation_epsilon                  */
+#define DPGICP_STOP_ABS_MSE           3u   /* |mse - mse_prev| < 1e-12                           */
+#define DPGICP_STOP_NO_CORRESPONDENCES 4u  /* fewer than 3 pairs: the only converged==false case */
+#define DPGICP_FLAG_CONVERGED         0x100u  /* == what icp.hasConverged() returns, dpg_slam.cc:445 */
+#define DPGICP_FLAG_COV_SINGULAR      0x200u  /* Hessian not invertible; cov fell back to the LIVE diagonal */
+#define DPGICP_FLAG_EMPTY_INPUT       0x400u  /* a cloud of the pair had no points                */
+
+/* ---- parameter block (defaults = src/dpg_slam/parameters.h, see dpgicp_default_params) ---- */
+typedef struct dpgicp_params {
+  int32_t max_iterations;              /* 500    parameters.h:146 */
+  int32_t use_reciprocal;              /* 1      parameters.h:201 */
+  int32_t ransac_iterations;           /* 50     parameters.h:191 — stored, inert (as in stock PCL ICP) */
+  int32_t downsample_divisor;          /* 5      parameters.h:402 — 1 = "1081-beam" benchmark setting */
+  int32_t metric;                      /* DPGICP_METRIC_*  (default point-to-point)              */
+  int32_t search;                      /* DPGICP_SEARCH_*  (default pruned)                      */
+  int32_t cov_mode;                    /* DPGICP_COV_*     (default REFERENCE_LIVE = drop-in)    */
+  int32_t cov_cap;                     /* 200    cov_func_point_to_point.h:307; 0 = no cap       */
+  double  transformation_epsilon;      /* 5e-9   parameters.h:159 */
+  double  max_correspondence_distance; /* 0.6    parameters.h:173 */
+  double  cov_sensor_variance;         /* 0.01   cov_func_point_to_point.h:554 (cov_z = 0.01 I)  */
+  float   laser_x_variance;            /* 0.5    parameters.h:374 */
+  float   laser_y_variance;            /* 0.5    parameters.h:385 */
+  float   laser_theta_variance;        /* 0.3    parameters.h:396 */
+  int32_t reserved0;
+} dpgicp_params;
+
+/* ---- fixed-size result record (112 bytes) ------------------------------------------------- */
+typedef struct dpgicp_result {
+  float    tx, ty;        /* T(0,3), T(1,3) of the final transform: pose of source in target frame */
+  float    theta;         /* atan2f(T(1,0), T(0,0))                       dpg_slam.cc:434-439       */
+  float    rot_c, rot_s;  /* T(0,0), T(1,0) — the raw rotation entries theta was taken from         */
+  int32_t  iterations;    /* ICP iterations executed                                               */
+  uint32_t status;        /* DPGICP_STOP_* | DPGICP_FLAG_*                                          */
+  int32_t  n_correspondences; /* of the last executed iteration                                    */
+  double   mse;           /* mean squared correspondence distance of the last executed iteration   */
+  double   cov[9];        /* 3x3, axes (x, y, theta), row-major (symmetric)  cov.h:564-566,573-575  */
+} dpgicp_result;
+
+typedef struct dpgicp_ctx dpgicp_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int  dpgicp_abi_version(void);
+int  dpgicp_default_params(dpgicp_params *p);
+int  dpgicp_create(int device_ordinal, dpgicp_ctx **out_ctx);
+void dpgicp_destroy(dpgicp_ctx *ctx);
+const char *dpgicp_last_error(const dpgicp_ctx *ctx);   /* ctx may be NULL: last create() error */
+
+/* Launch work of this context on an existing CUDA stream (a cudaStream_t passed as void*), e.g.
+ * the caller's framework stream so that its events bracket our kernels.  NULL = own stream.   */
+int  dpgicp_set_stream(dpgicp_ctx *ctx, void *cuda_stream);
+int  dpgicp_synchronize(dpgicp_ctx *ctx);
+
+/* ---- scan store (replaces the per-node cached clouds, dpg_node.cc:8-26) --------------------- */
+/* Upload n_scans ragged clouds.  Scan k owns points [offsets[k], offsets[k+1]) of `points`;
+ * a point is two consecutive floats (x, y) at byte stride `stride_bytes` (8 = packed float2,
+ * 16 = pcl::PointXYZ layout {x,y,z,pad}; z is ignored, the reference sets it to 0).
+ * Replaces any previous store.                                                                 */
+int  dpgicp_upload_scans(dpgicp_ctx *ctx, const void *points, size_t stride_bytes,
+                         const int64_t *offsets, int32_t n_scans);
+
+/* Upload raw range scans and convert on the device (createNode dpg_slam.cc:488-513 +
+ * getCachedPointCloudFromNode dpg_node.cc:8-26): angle_i = angle_inc*i + angle_min (float),
+ * p = (r cos a, r sin a), drop r >= range_max, then laser->base_link pose (lx, ly, ltheta).    */
+int  dpgicp_upload_ranges(dpgicp_ctx *ctx, const float *ranges, int32_t n_scans, int32_t n_beams,
+                          float angle_min, float angle_max, float range_max,
+                          float laser_x, float laser_y, float laser_theta);
+
+int  dpgicp_scan_count(const dpgicp_ctx *ctx);
+/* copy scan k of the store back to the host (packed float2); *n_points in = capacity, out = count */
+int  dpgicp_download_scan(dpgicp_ctx *ctx, int32_t scan, float *xy, int32_t *n_points);
+
+/* ---- batched alignment ---------------------------------------------------------------------- */
+/* The runIcp batch: pair k aligns source scan src_idx[k] (node_2) onto target scan tgt_idx[k]
+ * (node_1) starting from guess[3k..3k+2] = (dx, dy, dtheta), the pose of node_2 in node_1's frame
+ * (dpg_slam.cc:364-378).  Synchronous; writes n_pairs records to out (host memory).            */
+int  dpgicp_submit_pairs(dpgicp_ctx *ctx, const int32_t *src_idx, const int32_t *tgt_idx,
+                         const float *guess, int64_t n_pairs, const dpgicp_params *params,
+                         dpgicp_result *out);
+
+/* Same work split into resident steps (what the benchmark's device-resident figure times):      */
+int  dpgicp_set_pairs(dpgicp_ctx *ctx, const int32_t *src_idx, const int32_t *tgt_idx,
+                      const float *guess, int64_t n_pairs);            /* H2D of the pair list   */
+int  dpgicp_run(dpgicp_ctx *ctx, const dpgicp_params *params);         /* async on ctx stream    */
+int  dpgicp_fetch_results(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n_pairs); /* D2H + sync   */
+/* device address of the record array written by dpgicp_run (n_pairs * sizeof(dpgicp_result));
+ * lets a multi-GPU host gather records device-to-device (NCCL) without a host bounce.          */
+int  dpgicp_results_device_ptr(dpgicp_ctx *ctx, void **out_ptr, int64_t *out_n_pairs);
+/* executed-work counters of the last dpgicp_run, summed over pairs (after synchronisation):
+ * [0] iterations, [1] correspondences, [2] distance evaluations, [3] block tests, [4] kernel launches */
+int  dpgicp_last_run_counters(dpgicp_ctx *ctx, uint64_t counters[8]);
+
+/* ---- single-call shapes of the two reference functions -------------------------------------- */
+/* runIcp shape: two clouds + guess -> record.  source = node_2 cloud, target = node_1 cloud,
+ * both NOT yet down-sampled (params->downsample_divisor is applied inside, dpg_slam.cc:397-402). */
+int  dpgicp_single_pair(dpgicp_ctx *ctx,
+                        const void *source_points, int32_t n_source,
+                        const void *target_points, int32_t n_target, size_t stride_bytes,
+                        const float guess[3], const dpgicp_params *params, dpgicp_result *out);
+
+/* calculate_ICP_COV shape: data_pi, model_qi, Matrix4f (column-major 16 floats), three variances
+ * -> 3x3 double.  cov_mode LIVE reproduces the reference's live output; CENSI_INDEXPAIR its
+ * intended one (the clouds are paired by index, as the reference passes them).                  */
+int  dpgicp_cov(dpgicp_ctx *ctx,
+                const void *data_pi, int32_t n_data, const void *model_qi, int32_t n_model,
+                size_t stride_bytes, const float transform_colmajor[16],
+                const dpgicp_params *params, double cov_out[9], uint32_t *status_out);
+
+/* Host helper, no device work: the guess runIcp derives from two node pose estimates
+ * (dpg_slam.cc:364-370 = math_utils::inverseTransformPoint, math_utils.cc:20-34, and AngleMod,
+ * math_utils.h:13-16), in the reference's float arithmetic.  pose = (x, y, theta).             */
+int  dpgicp_relative_guess(const float node_1_pose[3], const float node_2_pose[3], float guess[3]);
+
+/* ---- parity / inspection hook ---------------------------------------------------------------- */
+/* One correspondence pass at a given iterate: the source cloud (already down-sampled) is
+ * transformed by T = [c -s tx; s c ty] exactly as one ICP iteration would, then matched.
+ * corr_tgt[i] = matched target index or -1; corr_d2[i] = squared distance (binary32).
+ * This is what the "correspondence sets bit-exact at equal iterate" tests call.                 */
+int  dpgicp_correspondences(dpgicp_ctx *ctx,
+                            const void *source_points, int32_t n_source,
+                            const void *target_points, int32_t n_target, size_t stride_bytes,
+                            const float T[4] /* c, s, tx, ty */, const dpgicp_params *params,
+                            int32_t *corr_tgt, float *corr_d2);
+
+/* ---- candidate-pair enumeration (callers' distance gate, dpg_slam.cc:91-98,275-282) ---------- */
+/* For node i (ascending) and every j < i-1 ... emits (src=i, tgt=j) when the node positions are
+ * within same_pass_radius (same pass) or other_pass_radius (different pass), plus every
+ * successive pair (src=i, tgt=i-1) — the pair set of one DpgSLAM::reoptimize().  Output order is
+ * the reference's loop order.  *n_pairs in = capacity, out = count (DPGICP_E_TOOBIG if short).  */
+int  dpgicp_enumerate_pairs(dpgicp_ctx *ctx, const float *node_xy, const int32_t *node_pass,
+                            int32_t n_nodes, float same_pass_radius, float other_pass_radius,
+                            int32_t *src_idx, int32_t *tgt_idx, int64_t *n_pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPGICP_H */

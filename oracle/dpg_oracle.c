@@ -1,0 +1,569 @@
+/*
+ * dpg_oracle.c — CPU restatement of DPG-SLAM's runIcp + calculate_ICP_COV.  TEST INFRASTRUCTURE;
+ * see dpg_oracle.h for who may use it and for the parity status (ICP loop: PARITY UNPINNED,
+ * PCL is absent; covariance: pinned against the compiled reference header).
+ *
+ * Build with -O2 -ffp-contract=off (no FMA contraction: the arithmetic contract below is stated
+ * in individually rounded IEEE-754 operations).
+ *
+ * ARITHMETIC CONTRACT (shared with the CUDA path, DESIGN.md §"arithmetic contract")
+ *   points            binary32 (x, y), |coord| <= 1000
+ *   transform         x' = ((c*x) + ((-s)*y)) + tx ; y' = ((s*x) + (c*y)) + ty      binary32, no FMA
+ *                     (Matrix4f * Vector4f evaluated column by column, PCL transformCloud)
+ *   distance          d2 = (dx*dx) + (dy*dy), dx = px - qx, dy = py - qy           binary32, no FMA
+ *                     (FLANN L2_Simple accumulates diff*diff in coordinate order; z term is +0)
+ *   nearest neighbour argmin over (d2, index) lexicographically  (lowest index wins ties)
+ *   gate              d2 <= fl32_floor(max_correspondence_distance^2 computed in binary64)
+ *   moment sums       exact int64 fixed point: round-to-nearest-even of value * 2^S
+ *                     S = 32 for sums of coordinates, 28 for sums of coordinate products,
+ *                     40 for the sum of squared distances  -> independent of summation order
+ *   rigid step        binary64, individually rounded ops, closed planar Procrustes (the z = 0
+ *                     case of PCL's Umeyama/SVD step), entries rounded to binary32
+ *   composition       final = step * final, binary32, k-ordered dot products, no FMA
+ */
+#include "dpg_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define SCALE_LIN  4294967296.0          /* 2^32 */
+#define SCALE_PROD 268435456.0           /* 2^28 */
+#define SCALE_D2   1099511627776.0       /* 2^40 */
+
+/* ------------------------------------------------------------------------------------------------
+ * a2. guess
+ * ---------------------------------------------------------------------------------------------- */
+
+/* math_utils.h:13-16 with T = float: the expression is evaluated in double (M_PI is double) and
+ * assigned back to the float. */
+float orc_angle_mod(float a) {
+  double d = (double)a;
+  d -= (M_PI * 2.0) * rint(d / (M_PI * 2.0));
+  return (float)d;
+}
+
+/* math_utils.cc:20-34 as called from dpg_slam.cc:364-368: src = node_2 pose, target frame = node_1.
+ * Eigen::Rotation2Df(-th1) takes cosf/sinf of the float angle; the 2x2 * 2x1 product is a
+ * k-ordered dot product in float. */
+void orc_relative_guess(const float p1[2], float th1, const float p2[2], float th2, float guess[3]) {
+  float tx = p2[0] - p1[0];
+  float ty = p2[1] - p1[1];
+  float ang = -th1;
+  float c = cosf(ang), s = sinf(ang);
+  float m01 = -s;
+  guess[0] = (c * tx) + (m01 * ty);
+  guess[1] = (s * tx) + (c * ty);
+  guess[2] = orc_angle_mod(th2 - th1);
+}
+
+/* dpg_slam.cc:374-378: `cos(est_angle_displ)` on a float argument inside a Matrix4f initialiser.
+ * Restated as the binary64 libm value rounded to binary32 (the ::cos(double) overload); the
+ * std::cos(float) overload differs by at most one binary32 ulp. */
+void orc_guess_matrix(const float guess[3], float T[4]) {
+  T[0] = (float)cos((double)guess[2]);
+  T[1] = (float)sin((double)guess[2]);
+  T[2] = guess[0];
+  T[3] = guess[1];
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * a3 / a4. scan -> cloud, down-sampling
+ * ---------------------------------------------------------------------------------------------- */
+
+/* createNode dpg_slam.cc:497-506: angle_inc = (max-min)/(n-1.0) [double divide, stored float],
+ * angle = angle_inc*i + angle_min in float.  MeasurementPoint dpg_measurement.h:41-46 labels
+ * range >= max_range MAX_RANGE; getPointInLaserFrame dpg_measurement.h:102-104 is
+ * (range*cos(angle), range*sin(angle)) — restated with the double overloads, rounded to float.
+ * getCachedPointCloudFromNode dpg_node.cc:13-22 skips MAX_RANGE and applies transformPoint
+ * (math_utils.cc:5-18): Rotation2Df(ltheta) * p + t. */
+int orc_ranges_to_cloud(const float *ranges, int n_beams, float angle_min, float angle_max,
+                        float range_max, float lx, float ly, float ltheta, float *xy) {
+  float angle_inc = (float)(((double)(float)(angle_max - angle_min)) / ((double)n_beams - 1.0));
+  float c = cosf(ltheta), s = sinf(ltheta);
+  float m01 = -s;
+  int n = 0;
+  for (int i = 0; i < n_beams; ++i) {
+    float r = ranges[i];
+    if (r >= range_max) continue;
+    float angle = angle_inc * (float)i + angle_min;
+    float px = (float)((double)r * cos((double)angle));
+    float py = (float)((double)r * sin((double)angle));
+    float rx = (c * px) + (m01 * py);
+    float ry = (s * px) + (c * py);
+    xy[2 * n + 0] = lx + rx;
+    xy[2 * n + 1] = ly + ry;
+    ++n;
+  }
+  return n;
+}
+
+/* dpg_slam.cc:346-360: keep compacted indices 0, d, 2d, ... */
+int orc_downsample(const float *xy, int n, int divisor, float *out_xy) {
+  if (divisor < 1) divisor = 1;
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (i % divisor == 0) {
+      out_xy[2 * m] = xy[2 * i];
+      out_xy[2 * m + 1] = xy[2 * i + 1];
+      ++m;
+    }
+  }
+  return m;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * a5. ICP building blocks (PCL semantics)
+ * ---------------------------------------------------------------------------------------------- */
+
+void orc_transform_points(const float T[4], const float *xy, int n, float *out_xy) {
+  const float c = T[0], s = T[1], tx = T[2], ty = T[3];
+  const float ms = -s;
+  for (int i = 0; i < n; ++i) {
+    float x = xy[2 * i], y = xy[2 * i + 1];
+    float nx = ((c * x) + (ms * y)) + tx;
+    float ny = ((s * x) + (c * y)) + ty;
+    out_xy[2 * i] = nx;
+    out_xy[2 * i + 1] = ny;
+  }
+}
+
+static inline float dist2(float ax, float ay, float bx, float by) {
+  float dx = ax - bx, dy = ay - by;
+  return (dx * dx) + (dy * dy);
+}
+
+/* largest binary32 value <= the binary64 threshold: `d2 > max_dist_sqr` (float vs double in PCL's
+ * correspondence_estimation.hpp) is then the same predicate as the float compare d2 > thr.       */
+static float gate_threshold(const dpgicp_params *p) {
+  double d = p->max_correspondence_distance * p->max_correspondence_distance;
+  float f = (float)d;
+  if ((double)f > d) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
+/* brute-force (d2, index) argmin of point (qx,qy) over a cloud */
+static inline void nn_brute(float qx, float qy, const float *cloud, int n, int *best_i, float *best_d) {
+  float bd = INFINITY;
+  int bi = -1;
+  for (int j = 0; j < n; ++j) {
+    float d = dist2(qx, qy, cloud[2 * j], cloud[2 * j + 1]);
+    if (d < bd) { bd = d; bi = j; }
+  }
+  *best_i = bi;
+  *best_d = bd;
+}
+
+/* --- exact uniform-grid search used only to time a non-strawman CPU baseline ------------------- */
+typedef struct {
+  double x0, y0, inv;
+  int nx, ny;
+  int *start;   /* nx*ny + 1 */
+  int *items;   /* n, point indices sorted by cell, ascending index inside a cell */
+} grid_t;
+
+static void grid_build(grid_t *g, const float *cloud, int n, double cell) {
+  double xmin = DBL_MAX, ymin = DBL_MAX, xmax = -DBL_MAX, ymax = -DBL_MAX;
+  for (int i = 0; i < n; ++i) {
+    double x = cloud[2 * i], y = cloud[2 * i + 1];
+    if (x < xmin) xmin = x;
+    if (x > xmax) xmax = x;
+    if (y < ymin) ymin = y;
+    if (y > ymax) ymax = y;
+  }
+  if (n == 0) { xmin = ymin = 0; xmax = ymax = 0; }
+  g->x0 = xmin; g->y0 = ymin; g->inv = 1.0 / cell;
+  g->nx = (int)floor((xmax - xmin) * g->inv) + 1;
+  g->ny = (int)floor((ymax - ymin) * g->inv) + 1;
+  int cells = g->nx * g->ny;
+  g->start = (int *)calloc((size_t)cells + 1, sizeof(int));
+  g->items = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; ++i) {
+    int cx = (int)floor((cloud[2 * i] - g->x0) * g->inv);
+    int cy = (int)floor((cloud[2 * i + 1] - g->y0) * g->inv);
+    g->start[cy * g->nx + cx + 1]++;
+  }
+  for (int c = 0; c < cells; ++c) g->start[c + 1] += g->start[c];
+  int *fill = (int *)malloc(sizeof(int) * (size_t)(cells > 0 ? cells : 1));
+  memcpy(fill, g->start, sizeof(int) * (size_t)cells);
+  for (int i = 0; i < n; ++i) {
+    int cx = (int)floor((cloud[2 * i] - g->x0) * g->inv);
+    int cy = (int)floor((cloud[2 * i + 1] - g->y0) * g->inv);
+    g->items[fill[cy * g->nx + cx]++] = i;
+  }
+  free(fill);
+}
+
+static void grid_free(grid_t *g) { free(g->start); free(g->items); }
+
+/* (d2, index) argmin restricted to the 3x3 cells around the query.  With cell > gate distance every
+ * point whose computed d2 passes the gate lies in those cells, so after gating the answer equals
+ * the brute-force one (a best candidate with d2 > thr is reported as "no neighbour" either way). */
+static inline void nn_grid(const grid_t *g, float qx, float qy, const float *cloud, int *best_i, float *best_d) {
+  float bd = INFINITY;
+  int bi = -1;
+  int cx = (int)floor(((double)qx - g->x0) * g->inv);
+  int cy = (int)floor(((double)qy - g->y0) * g->inv);
+  for (int yy = cy - 1; yy <= cy + 1; ++yy) {
+    if (yy < 0 || yy >= g->ny) continue;
+    for (int xx = cx - 1; xx <= cx + 1; ++xx) {
+      if (xx < 0 || xx >= g->nx) continue;
+      int c = yy * g->nx + xx;
+      for (int k = g->start[c]; k < g->start[c + 1]; ++k) {
+        int j = g->items[k];
+        float d = dist2(qx, qy, cloud[2 * j], cloud[2 * j + 1]);
+        if (d < bd || (d == bd && j < bi)) { bd = d; bi = j; }
+      }
+    }
+  }
+  *best_i = bi;
+  *best_d = bd;
+}
+
+/* PCL CorrespondenceEstimation::determine[Reciprocal]Correspondences (Appendix A.3-2): for each
+ * source index in order: forward NN, gate, reciprocal NN over the *current* source, require i' == i. */
+int orc_correspondences(const float *src_t, int ns, const float *tgt, int nt,
+                        const dpgicp_params *p, int fast, int32_t *corr, float *d2) {
+  const float thr = gate_threshold(p);
+  int K = 0;
+  if (ns <= 0 || nt <= 0) {
+    for (int i = 0; i < ns; ++i) { corr[i] = -1; if (d2) d2[i] = INFINITY; }
+    return 0;
+  }
+  grid_t gt, gs;
+  if (fast) {
+    double cell = p->max_correspondence_distance * 1.001;
+    grid_build(&gt, tgt, nt, cell);
+    if (p->use_reciprocal) grid_build(&gs, src_t, ns, cell);
+  }
+  for (int i = 0; i < ns; ++i) {
+    int j, ir;
+    float d, dr;
+    corr[i] = -1;
+    if (fast) nn_grid(&gt, src_t[2 * i], src_t[2 * i + 1], tgt, &j, &d);
+    else nn_brute(src_t[2 * i], src_t[2 * i + 1], tgt, nt, &j, &d);
+    if (d2) d2[i] = d;
+    if (j < 0 || d > thr) continue;
+    if (p->use_reciprocal) {
+      if (fast) nn_grid(&gs, tgt[2 * j], tgt[2 * j + 1], src_t, &ir, &dr);
+      else nn_brute(tgt[2 * j], tgt[2 * j + 1], src_t, ns, &ir, &dr);
+      if (dr > thr || ir != i) continue;
+    }
+    corr[i] = j;
+    ++K;
+  }
+  if (fast) {
+    grid_free(&gt);
+    if (p->use_reciprocal) grid_free(&gs);
+  }
+  return K;
+}
+
+/* exact fixed-point moment sums of one correspondence set */
+typedef struct {
+  int64_t spx, spy, sqx, sqy;     /* 2^32 */
+  int64_t sxx, sxy, syx, syy;     /* 2^28: sum px*qx, px*qy, py*qx, py*qy */
+  int64_t sd2;                    /* 2^40 */
+  int32_t k;
+} moments_t;
+
+static inline int64_t fx(double v) { return (int64_t)llrint(v); }   /* round-to-nearest-even */
+
+static void accumulate_moments(const float *src_t, const float *tgt, int ns,
+                               const int32_t *corr, const float *d2, moments_t *m) {
+  memset(m, 0, sizeof(*m));
+  for (int i = 0; i < ns; ++i) {
+    int j = corr[i];
+    if (j < 0) continue;
+    double px = src_t[2 * i], py = src_t[2 * i + 1];
+    double qx = tgt[2 * j], qy = tgt[2 * j + 1];
+    m->spx += fx(px * SCALE_LIN);
+    m->spy += fx(py * SCALE_LIN);
+    m->sqx += fx(qx * SCALE_LIN);
+    m->sqy += fx(qy * SCALE_LIN);
+    m->sxx += fx((px * qx) * SCALE_PROD);
+    m->sxy += fx((px * qy) * SCALE_PROD);
+    m->syx += fx((py * qx) * SCALE_PROD);
+    m->syy += fx((py * qy) * SCALE_PROD);
+    m->sd2 += fx((double)d2[i] * SCALE_D2);
+    m->k++;
+  }
+}
+
+/* PCL TransformationEstimationSVD on z = 0 data == planar Procrustes (Appendix A.3-5, A.6).
+ * step = (c, s, tx, ty) in binary32. */
+static void solve_rigid_p2p(const moments_t *m, float step[4]) {
+  const double K = (double)m->k;
+  const double spx = (double)m->spx * (1.0 / SCALE_LIN);
+  const double spy = (double)m->spy * (1.0 / SCALE_LIN);
+  const double sqx = (double)m->sqx * (1.0 / SCALE_LIN);
+  const double sqy = (double)m->sqy * (1.0 / SCALE_LIN);
+  const double dot = (double)(m->sxx + m->syy) * (1.0 / SCALE_PROD);
+  const double crs = (double)(m->sxy - m->syx) * (1.0 / SCALE_PROD);
+  const double a = dot - ((spx * sqx) + (spy * sqy)) / K;
+  const double b = crs - ((spx * sqy) - (spy * sqx)) / K;
+  const double h = sqrt((a * a) + (b * b));
+  double c = 1.0, s = 0.0;
+  if (h > 0.0) { c = a / h; s = b / h; }
+  const double mpx = spx / K, mpy = spy / K, mqx = sqx / K, mqy = sqy / K;
+  const double tx = mqx - ((c * mpx) - (s * mpy));
+  const double ty = mqy - ((s * mpx) + (c * mpy));
+  step[0] = (float)c;
+  step[1] = (float)s;
+  step[2] = (float)tx;
+  step[3] = (float)ty;
+}
+
+/* final = step * final on the (c, s, tx, ty) parametrisation of the Matrix4f product (A.3-6) */
+static void compose(const float st[4], float fin[4]) {
+  const float c = st[0], s = st[1], ms = -st[1];
+  float nc = (c * fin[0]) + (ms * fin[1]);
+  float ns = (s * fin[0]) + (c * fin[1]);
+  float ntx = ((c * fin[2]) + (ms * fin[3])) + st[2];
+  float nty = ((s * fin[2]) + (c * fin[3])) + st[3];
+  fin[0] = nc; fin[1] = ns; fin[2] = ntx; fin[3] = nty;
+}
+
+void orc_icp(const float *src, int ns, const float *tgt, int nt, const float guess[3],
+             const dpgicp_params *p, int fast, dpgicp_result *out, orc_trace *trace) {
+  float fin[4];
+  orc_guess_matrix(guess, fin);
+  out->iterations = 0;
+  out->n_correspondences = 0;
+  out->mse = 0.0;
+  uint32_t status = DPGICP_STOP_NONE;
+  if (trace) trace->count = 0;
+
+  float *cur = (float *)malloc(sizeof(float) * 2 * (size_t)(ns > 0 ? ns : 1));
+  int32_t *corr = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ns > 0 ? ns : 1));
+  float *d2 = (float *)malloc(sizeof(float) * (size_t)(ns > 0 ? ns : 1));
+  /* A.2: the guess is applied to the source once, then steps are applied incrementally */
+  orc_transform_points(fin, src, ns, cur);
+
+  if (ns <= 0 || nt <= 0) status |= DPGICP_FLAG_EMPTY_INPUT;
+
+  double mse_prev = DBL_MAX;
+  const double rot_thr = 1.0 - p->transformation_epsilon;
+  for (;;) {
+    if (trace && trace->count < trace->capacity) {
+      memcpy(trace->T_iter + 4 * trace->count, fin, sizeof(fin));
+    }
+    int K = orc_correspondences(cur, ns, tgt, nt, p, fast, corr, d2);
+    if (trace && trace->count < trace->capacity) trace->n_corr[trace->count++] = K;
+    out->n_correspondences = K;
+    if (K < 3) {                                   /* A.3-4: min_number_correspondences_ = 3 */
+      status |= DPGICP_STOP_NO_CORRESPONDENCES;
+      break;
+    }
+    moments_t m;
+    accumulate_moments(cur, tgt, ns, corr, d2, &m);
+    float st[4];
+    solve_rigid_p2p(&m, st);
+    orc_transform_points(st, cur, ns, cur);        /* A.3-6 */
+    compose(st, fin);
+    out->iterations++;
+    out->mse = ((double)m.sd2 * (1.0 / SCALE_D2)) / (double)m.k;
+
+    /* A.5 DefaultConvergenceCriteria, in PCL's order */
+    if (out->iterations >= p->max_iterations) {
+      status |= DPGICP_STOP_ITERATIONS | DPGICP_FLAG_CONVERGED;
+      break;
+    }
+    float tr = ((st[0] + st[0]) + 1.0f) - 1.0f;    /* coeff(0,0)+coeff(1,1)+coeff(2,2)-1 in float */
+    double cos_angle = 0.5 * (double)tr;
+    float tsq = (st[2] * st[2]) + (st[3] * st[3]); /* float arithmetic, then compared as double */
+    if (cos_angle >= rot_thr && (double)tsq <= p->transformation_epsilon) {
+      status |= DPGICP_STOP_TRANSFORM | DPGICP_FLAG_CONVERGED;
+      break;
+    }
+    if (fabs(out->mse - mse_prev) < 1e-12) {
+      status |= DPGICP_STOP_ABS_MSE | DPGICP_FLAG_CONVERGED;
+      break;
+    }
+    mse_prev = out->mse;
+  }
+  out->rot_c = fin[0];
+  out->rot_s = fin[1];
+  out->tx = fin[2];
+  out->ty = fin[3];
+  out->theta = atan2f(fin[1], fin[0]);             /* Rotation2Df::fromRotationMatrix().angle() */
+  out->status = status;
+  free(cur); free(corr); free(d2);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * a6. covariance — planar closed form of cov_func_point_to_point.h
+ * ---------------------------------------------------------------------------------------------- */
+
+static int inv3_sym(const double H[9], double Hi[9]) {
+  const double a = H[0], b = H[1], c = H[2], d = H[4], e = H[5], f = H[8];
+  const double c00 = d * f - e * e;
+  const double c01 = c * e - b * f;
+  const double c02 = b * e - c * d;
+  const double det = a * c00 + b * c01 + c * c02;
+  if (!(fabs(det) > 0.0) || !isfinite(det)) return 0;
+  const double id = 1.0 / det;
+  Hi[0] = c00 * id; Hi[1] = c01 * id; Hi[2] = c02 * id;
+  Hi[3] = Hi[1];    Hi[4] = (a * f - c * c) * id; Hi[5] = (b * c - a * e) * id;
+  Hi[6] = Hi[2];    Hi[7] = Hi[5]; Hi[8] = (a * d - b * b) * id;
+  for (int i = 0; i < 9; ++i) if (!isfinite(Hi[i])) return 0;
+  return 1;
+}
+
+uint32_t orc_cov_censi(const float *P, const float *Q, int n_h, int n_d, const float T[4],
+                       double sensor_var, const float live_diag[3], double cov[9], double H3[9]) {
+  /* cov.h:26-35: x, y are the float entries widened; a = (double)atan2f(T(1,0), T(0,0)) */
+  const double x = (double)T[2], y = (double)T[3];
+  const double a = (double)atan2f(T[1], T[0]);
+  const double c = cos(a), s = sin(a);
+  double H[9] = {0};
+  for (int k = 0; k < n_h; ++k) {                 /* cov.h:45-283 restricted to rows/cols (0,1,3) */
+    const double px = P[2 * k], py = P[2 * k + 1], qx = Q[2 * k], qy = Q[2 * k + 1];
+    const double A = px * c - py * s, B = px * s + py * c;
+    const double dx = x - qx, dy = y - qy;
+    H[0] += 2.0;           H[2] += -2.0 * B;
+    H[4] += 2.0;           H[5] += 2.0 * A;
+    H[8] += -2.0 * (A * dx + B * dy);
+  }
+  H[1] = H[3] = 0.0; H[6] = H[2]; H[7] = H[5];
+  double M[9] = {0};
+  for (int k = 0; k < n_d; ++k) {                 /* cov.h:311-530 restricted the same way */
+    const double px = P[2 * k], py = P[2 * k + 1], qx = Q[2 * k], qy = Q[2 * k + 1];
+    const double A = px * c - py * s, B = px * s + py * c;
+    const double dx = x - qx, dy = y - qy;
+    const double D[3][4] = {
+        {2.0 * c, -2.0 * s, -2.0, 0.0},
+        {2.0 * s, 2.0 * c, 0.0, -2.0},
+        {2.0 * (-s * dx + c * dy), -2.0 * (c * dx + s * dy), 2.0 * B, -2.0 * A}};
+    for (int r = 0; r < 3; ++r)
+      for (int q = 0; q < 3; ++q) {
+        double acc = 0.0;
+        for (int z = 0; z < 4; ++z) acc += D[r][z] * D[q][z];
+        M[3 * r + q] += acc;
+      }
+  }
+  if (H3) memcpy(H3, H, sizeof(H));
+  double Hi[9];
+  if (n_h <= 0 || !inv3_sym(H, Hi)) {
+    memset(cov, 0, 9 * sizeof(double));
+    cov[0] = live_diag[0]; cov[4] = live_diag[1]; cov[8] = live_diag[2];
+    return DPGICP_FLAG_COV_SINGULAR;
+  }
+  /* cov.h:553-560: Hinv * D * (0.01 I) * D^T * Hinv */
+  double Tm[9];
+  for (int r = 0; r < 3; ++r)
+    for (int q = 0; q < 3; ++q) {
+      double acc = 0.0;
+      for (int z = 0; z < 3; ++z) acc += Hi[3 * r + z] * M[3 * z + q];
+      Tm[3 * r + q] = acc;
+    }
+  for (int r = 0; r < 3; ++r)
+    for (int q = 0; q < 3; ++q) {
+      double acc = 0.0;
+      for (int z = 0; z < 3; ++z) acc += Tm[3 * r + z] * Hi[3 * z + q];
+      cov[3 * r + q] = sensor_var * acc;
+    }
+  for (int i = 0; i < 9; ++i)
+    if (!isfinite(cov[i])) {
+      memset(cov, 0, 9 * sizeof(double));
+      cov[0] = live_diag[0]; cov[4] = live_diag[1]; cov[8] = live_diag[2];
+      return DPGICP_FLAG_COV_SINGULAR;
+    }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * a1. runIcp restated (dpg_slam.cc:362-446)
+ * ---------------------------------------------------------------------------------------------- */
+void orc_run_pair(const float *source_full, int n_source, const float *target_full, int n_target,
+                  const float guess[3], const dpgicp_params *p, int fast, dpgicp_result *out) {
+  memset(out, 0, sizeof(*out));
+  const int div = p->downsample_divisor < 1 ? 1 : p->downsample_divisor;
+  float *src = (float *)malloc(sizeof(float) * 2 * (size_t)(n_source > 0 ? n_source : 1));
+  float *tgt = (float *)malloc(sizeof(float) * 2 * (size_t)(n_target > 0 ? n_target : 1));
+  const int ns = orc_downsample(source_full, n_source, div, src);     /* dpg_slam.cc:397-402 */
+  const int nt = orc_downsample(target_full, n_target, div, tgt);
+  orc_icp(src, ns, tgt, nt, guess, p, fast, out, NULL);               /* dpg_slam.cc:404-416 */
+
+  const float live[3] = {p->laser_x_variance, p->laser_y_variance, p->laser_theta_variance};
+  const float T[4] = {out->rot_c, out->rot_s, out->tx, out->ty};
+  memset(out->cov, 0, sizeof(out->cov));
+  if (p->cov_mode == DPGICP_COV_REFERENCE_LIVE) {                      /* cov.h:572-575 */
+    out->cov[0] = live[0]; out->cov[4] = live[1]; out->cov[8] = live[2];
+  } else if (p->cov_mode == DPGICP_COV_CENSI_INDEXPAIR) {
+    /* dpg_slam.cc:429-431 passes the FULL clouds, paired by index; bound by the shorter cloud
+     * (the reference reads out of bounds when N1 < N2) */
+    int nh = n_source < n_target ? n_source : n_target;
+    int nd = nh;
+    if (p->cov_cap > 0 && nd > p->cov_cap) nd = p->cov_cap;           /* cov.h:307 */
+    out->status |= orc_cov_censi(source_full, target_full, nh, nd, T, p->cov_sensor_variance, live,
+                                 out->cov, NULL);
+  } else {
+    /* CENSI_CORR: correspondences at the final pose, in source order */
+    float *cur = (float *)malloc(sizeof(float) * 2 * (size_t)(ns > 0 ? ns : 1));
+    int32_t *corr = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ns > 0 ? ns : 1));
+    float *P = (float *)malloc(sizeof(float) * 2 * (size_t)(ns > 0 ? ns : 1));
+    float *Q = (float *)malloc(sizeof(float) * 2 * (size_t)(ns > 0 ? ns : 1));
+    orc_transform_points(T, src, ns, cur);
+    orc_correspondences(cur, ns, tgt, nt, p, fast, corr, NULL);
+    int k = 0;
+    for (int i = 0; i < ns; ++i)
+      if (corr[i] >= 0) {
+        P[2 * k] = src[2 * i]; P[2 * k + 1] = src[2 * i + 1];
+        Q[2 * k] = tgt[2 * corr[i]]; Q[2 * k + 1] = tgt[2 * corr[i] + 1];
+        ++k;
+      }
+    int nd = k;
+    if (p->cov_cap > 0 && nd > p->cov_cap) nd = p->cov_cap;
+    out->status |= orc_cov_censi(P, Q, k, nd, T, p->cov_sensor_variance, live, out->cov, NULL);
+    free(cur); free(corr); free(P); free(Q);
+  }
+  free(src); free(tgt);
+}
+
+int orc_run_batch(const float *points, const int64_t *offsets, int n_scans,
+                  const int32_t *src_idx, const int32_t *tgt_idx, const float *guess,
+                  int64_t n_pairs, const dpgicp_params *p, int fast, int threads,
+                  dpgicp_result *out) {
+  (void)n_scans;
+  int used = 1;
+#ifdef _OPENMP
+  if (threads < 1) threads = omp_get_max_threads();
+  used = threads;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads)
+#endif
+  for (int64_t k = 0; k < n_pairs; ++k) {
+    const int s = src_idx[k], t = tgt_idx[k];
+    orc_run_pair(points + 2 * offsets[s], (int)(offsets[s + 1] - offsets[s]),
+                 points + 2 * offsets[t], (int)(offsets[t + 1] - offsets[t]),
+                 guess + 3 * k, p, fast, out + k);
+  }
+  return used;
+}
+
+/* dpg_slam.cc:79-107 (reoptimize): for node i > 0: the successive pair (i-1 -> i), then every
+ * j < i-1 whose float distance passes the same-pass / other-pass gate.  source = node i. */
+int64_t orc_enumerate_pairs(const float *node_xy, const int32_t *node_pass, int n_nodes,
+                            float same_pass_radius, float other_pass_radius,
+                            int32_t *src_idx, int32_t *tgt_idx, int64_t capacity) {
+  int64_t n = 0;
+  for (int i = 1; i < n_nodes; ++i) {
+    if (n < capacity) { src_idx[n] = i; tgt_idx[n] = i - 1; }
+    ++n;
+    for (int j = 0; j < i - 1; ++j) {
+      float dx = node_xy[2 * j] - node_xy[2 * i];
+      float dy = node_xy[2 * j + 1] - node_xy[2 * i + 1];
+      float dist = sqrtf((dx * dx) + (dy * dy));
+      float thr = (node_pass[j] == node_pass[i]) ? same_pass_radius : other_pass_radius;
+      if (dist <= thr) {
+        if (n < capacity) { src_idx[n] = i; tgt_idx[n] = j; }
+        ++n;
+      }
+    }
+  }
+  return n;
+}
