@@ -97,7 +97,7 @@ EXPORTS = [
     "dpgicp_upload_ranges", "dpgicp_scan_count", "dpgicp_download_scan", "dpgicp_submit_pairs",
     "dpgicp_set_pairs", "dpgicp_run", "dpgicp_fetch_results", "dpgicp_results_device_ptr",
     "dpgicp_last_run_counters", "dpgicp_single_pair", "dpgicp_cov", "dpgicp_correspondences",
-    "dpgicp_enumerate_pairs", "dpgicp_relative_guess",
+    "dpgicp_enumerate_pairs", "dpgicp_relative_guess", "dpgicp_fp32_probe",
 ]
 
 _lib = None
@@ -142,6 +142,7 @@ def load_library() -> C.CDLL:
         "dpgicp_cov": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, vp, C.POINTER(C.c_uint32)]),
         "dpgicp_correspondences": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, vp, vp]),
         "dpgicp_relative_guess": (C.c_int, [vp, vp, vp]),
+        "dpgicp_fp32_probe": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "dpgicp_enumerate_pairs": (C.c_int, [vp, vp, vp, i32, C.c_float, C.c_float, vp, vp,
                                               C.POINTER(i64)]),
     }

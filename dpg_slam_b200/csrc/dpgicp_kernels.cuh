@@ -863,4 +863,27 @@ __global__ void enumerate_fill_kernel(const float2 *xy, const int32_t *pass, int
     if (gate_pair(xy, pass, i, j, r_same, r_other)) { src[o] = i; tgt[o] = j; ++o; }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * FP32-pipe probe: the roofline denominator of the distance loop, measured on the device in use.
+ * 8 independent dependent-chains per thread of separately rounded FMUL + FADD (the instruction mix
+ * the bit-exact distance loop is allowed to use; FMA = false) or of FFMA (FMA = true, for context).
+ * ---------------------------------------------------------------------------------------------- */
+template <bool FMA>
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float *out, int iters, float a, float b) {
+  float x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (FMA) x[k] = __fmaf_rn(x[k], a, b);
+      else x[k] = __fadd_rn(__fmul_rn(x[k], a), b);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += x[k];
+  if (s == 123.456f) out[0] = s;       /* keeps the chains alive; practically never true */
+}
+
 }  // namespace dpg

@@ -171,6 +171,12 @@ class ScanMatcher:
         return {"iterations": int(c[0]), "correspondences": int(c[1]), "distance_evals": int(c[2]),
                 "box_tests": int(c[3]), "kernel_launches": int(c[4])}
 
+    def fp32_probe(self) -> dict:
+        """Measured FP32 CUDA-core rates of this GPU (ops/s): separately rounded FMUL+FADD and FFMA."""
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self._lib.dpgicp_fp32_probe(self._h, C.byref(a), C.byref(b)))
+        return {"mul_add_ops_per_s": a.value, "fma_ops_per_s": b.value}
+
     # ---- the two reference call shapes ----------------------------------------------------------------
     def run_icp(self, node_1_cloud, node_2_cloud, guess, params: Optional[Params] = None):
         """``runIcp(node_1, node_2, icp_results)``: aligns node_2's cloud (source) onto node_1's

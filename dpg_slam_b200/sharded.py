@@ -1,0 +1,132 @@
+"""Multi-GPU form of the batch: scan pairs sharded round-robin, records gathered back.
+
+Scan pairs are independent until the pose-graph update (reference src/dpg_slam/dpg_slam.cc:119,313
+run optimizeGraph only after every runIcp call of the step), so pair ``k`` goes to rank
+``k % world`` with the scan store replicated on every GPU and NO data-path collective.  The only
+exchange is the final gather of the fixed-size result records (112 B each) that the host-side
+pose-graph update consumes: one ``all_gather`` over NCCL (NVLink/NVSwitch) on the device buffer the
+kernel wrote, or over gloo on host arrays in the CPU tests.
+
+One process per GPU (``torch.distributed``); torch is plumbing here (process group, device
+tensors), the arithmetic is the C-ABI library's.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from ._abi import RESULT_DTYPE
+
+RECORD_BYTES = RESULT_DTYPE.itemsize
+
+
+def shard_indices(n_pairs: int, rank: int, world: int) -> np.ndarray:
+    """Global pair indices owned by ``rank``: k with k % world == rank, ascending."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return np.arange(rank, n_pairs, world, dtype=np.int64)
+
+
+def shard_len(n_pairs: int, rank: int, world: int) -> int:
+    return (n_pairs - rank + world - 1) // world if n_pairs > rank else 0
+
+
+def padded_len(n_pairs: int, world: int) -> int:
+    """Records per rank in the gathered buffer (every rank contributes the same count)."""
+    return (n_pairs + world - 1) // world
+
+
+def interleave(gathered: np.ndarray, n_pairs: int, world: int) -> np.ndarray:
+    """``gathered`` is (world, padded_len) records in rank-major order -> global pair order.
+    Record k sits at [k % world, k // world]; the transpose view makes that a plain reshape."""
+    g = np.asarray(gathered).reshape(world, padded_len(n_pairs, world))
+    return np.ascontiguousarray(g.T).reshape(-1)[:n_pairs]
+
+
+class _DevMem:
+    """Minimal ``__cuda_array_interface__`` holder for a raw device pointer (no ownership)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+def device_bytes_tensor(ptr: int, nbytes: int, device):
+    import torch
+    return torch.as_tensor(_DevMem(ptr, nbytes), device=device)
+
+
+def gather_records(local: np.ndarray, n_pairs: int, rank: int, world: int, group=None,
+                   device_ptr: Optional[int] = None, device=None) -> np.ndarray:
+    """All-gather the per-rank record arrays and return all ``n_pairs`` records in global order on
+    every rank.  ``local`` holds this rank's ``shard_len`` records (host); when ``device_ptr`` is
+    given (the address from ``dpgicp_results_device_ptr``) the gather runs device-to-device over
+    NCCL without a host bounce and ``local`` may be None."""
+    import torch
+    import torch.distributed as dist
+
+    m = padded_len(n_pairs, world)
+    mine = shard_len(n_pairs, rank, world)
+    if device_ptr is not None:
+        send = torch.zeros(m * RECORD_BYTES, dtype=torch.uint8, device=device)
+        if mine:
+            send[:mine * RECORD_BYTES].copy_(device_bytes_tensor(device_ptr, mine * RECORD_BYTES, device))
+        recv = torch.empty(world * m * RECORD_BYTES, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        host = recv.cpu().numpy()
+    else:
+        buf = np.zeros(m, RESULT_DTYPE)
+        if mine:
+            buf[:mine] = local[:mine]
+        send = torch.from_numpy(buf.view(np.uint8).copy())
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send, group=group)
+        host = torch.cat(parts).numpy()
+    return interleave(host.view(RESULT_DTYPE), n_pairs, world)
+
+
+class ShardedScanMatcher:
+    """One rank's view of the sharded batch: replicated scan store, round-robin pair shard.
+
+    ``matcher`` is this rank's :class:`dpg_slam_b200.scanmatch.ScanMatcher` (one GPU).  The matcher
+    must run on the torch stream the collective is issued on (``matcher.set_stream``) so that the
+    gather is ordered after the kernel without a host synchronisation."""
+
+    def __init__(self, matcher, rank: int, world: int, group=None, device=None):
+        self.sm, self.rank, self.world, self.group, self.device = matcher, rank, world, group, device
+        self.n_pairs = 0
+        self._send = self._recv = None
+
+    def set_pairs(self, src_idx, tgt_idx, guess):
+        """Takes the GLOBAL pair list; keeps this rank's shard resident on its GPU."""
+        import torch
+        self.n_pairs = int(len(src_idx))
+        idx = shard_indices(self.n_pairs, self.rank, self.world)
+        g = np.ascontiguousarray(guess, np.float32).reshape(-1, 3)
+        self.sm.set_pairs(np.asarray(src_idx)[idx], np.asarray(tgt_idx)[idx], g[idx])
+        m = padded_len(self.n_pairs, self.world)
+        self._send = torch.zeros(m * RECORD_BYTES, dtype=torch.uint8, device=self.device)
+        self._recv = torch.empty(self.world * m * RECORD_BYTES, dtype=torch.uint8, device=self.device)
+
+    def run(self, params):
+        self.sm.run(params)
+
+    def gather_device(self):
+        """NCCL all-gather straight from the kernel's record buffer (device to device, asynchronous on
+        the current torch stream).  Returns the (world * padded_len * 112)-byte device tensor in
+        rank-major order."""
+        import torch.distributed as dist
+        ptr, n = self.sm.results_device_ptr()
+        mine = shard_len(self.n_pairs, self.rank, self.world)
+        assert n == mine
+        if mine:
+            self._send[:mine * RECORD_BYTES].copy_(device_bytes_tensor(ptr, mine * RECORD_BYTES, self.device),
+                                                   non_blocking=True)
+        dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+        return self._recv
+
+    def gather(self) -> np.ndarray:
+        """All ``n_pairs`` records in global pair order, on the host, on every rank."""
+        host = self.gather_device().cpu().numpy()
+        return interleave(host.view(RESULT_DTYPE), self.n_pairs, self.world)

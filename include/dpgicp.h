@@ -194,6 +194,12 @@ int  dpgicp_enumerate_pairs(dpgicp_ctx *ctx, const float *node_xy, const int32_t
                             int32_t n_nodes, float same_pass_radius, float other_pass_radius,
                             int32_t *src_idx, int32_t *tgt_idx, int64_t *n_pairs);
 
+/* ---- measurement aid ------------------------------------------------------------------------- */
+/* Measures this device's FP32 CUDA-core throughput with the two instruction mixes that matter for
+ * the roofline of the distance loop: separately rounded FMUL+FADD (what the bit-exact loop may use)
+ * and FFMA (for context).  Results in operations per second (one FMUL, FADD or FFMA = 1 op).     */
+int  dpgicp_fp32_probe(dpgicp_ctx *ctx, double *ops_per_s_mul_add, double *ops_per_s_fma);
+
 #ifdef __cplusplus
 }
 #endif

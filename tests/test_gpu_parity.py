@@ -1,0 +1,346 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs.  Bars (BASELINE.json north_star): correspondence index sets bit-exact at equal iterate;
+poses within 1e-5 m / 1e-5 rad; covariances within 1e-4 relative.  Because both sides follow one
+arithmetic contract, most fields are in fact compared bit for bit; the tolerances are
+written where the device's libm (atan2f, cos/sin in the covariance) may differ from glibc's."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from dpg_slam_b200 import _abi, synth
+from dpg_slam_b200._abi import (COV_CENSI_CORR, COV_CENSI_INDEXPAIR, COV_REFERENCE_LIVE, FLAG_CONVERGED,
+                                FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT, SEARCH_BRUTE, SEARCH_PRUNED, STOP_ITERATIONS,
+                                STOP_MASK, STOP_NO_CORRESPONDENCES, Params)
+from dpg_slam_b200.scanmatch import DpgIcpError
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_M = 1e-5        # north_star: final poses agree within 1e-5 m / 1e-5 rad
+POSE_TOL_RAD = 1e-5
+COV_REL_TOL = 1e-4       # north_star: covariances agree within 1e-4 relative
+EXACT_FIELDS = ("tx", "ty", "rot_c", "rot_s", "iterations", "status", "n_correspondences", "mse")
+
+
+def assert_records_match(got, ref, ctx=""):
+    assert len(got) == len(ref)
+    for f in EXACT_FIELDS:                      # same arithmetic contract on both sides -> same bits
+        bad = np.nonzero(got[f] != ref[f])[0]
+        assert bad.size == 0, f"{ctx}: field {f} differs at pairs {bad[:5]}: {got[f][bad[:5]]} vs {ref[f][bad[:5]]}"
+    assert np.max(np.abs(got["tx"] - ref["tx"]), initial=0) <= POSE_TOL_M
+    assert np.max(np.abs(got["ty"] - ref["ty"]), initial=0) <= POSE_TOL_M
+    dth = np.abs(got["theta"] - ref["theta"])
+    dth = np.minimum(dth, np.abs(dth - 2 * np.pi))
+    assert np.max(dth, initial=0) <= POSE_TOL_RAD, ctx
+    scale = np.abs(ref["cov"]).max(axis=1)
+    rel = np.abs(got["cov"] - ref["cov"]).max(axis=1) / np.where(scale > 0, scale, 1.0)
+    assert np.max(rel, initial=0) <= COV_REL_TOL, f"{ctx}: cov rel err {rel.max():.3e}"
+
+
+def run_both(sm, wl, p, threads=0):
+    sm.upload_ranges(wl.ranges, wl.scanner)
+    pts, off = sm.download_store()
+    got = sm.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+    ref, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, p, fast=1, threads=threads)
+    return got, ref, pts, off
+
+
+# ---- scan store ------------------------------------------------------------------------------------------
+def test_upload_ranges_matches_oracle_cloud_bit_exact(gpu_matcher):
+    wl = synth.config_loop_closure(n_pairs=4, n_scans=24, seed=21)
+    wl.ranges[3, ::7] = wl.scanner.range_max            # ragged: extra dropped beams
+    wl.ranges[5, :] = wl.scanner.range_max + 1          # an empty scan
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    assert gpu_matcher.scan_count == 24
+    for k in range(24):
+        want = O.ranges_to_cloud(wl.ranges[k], wl.scanner)
+        got = gpu_matcher.download_scan(k)
+        assert got.shape == want.shape and got.tobytes() == want.tobytes(), k
+    assert gpu_matcher.download_scan(5).shape == (0, 2)
+
+
+def test_upload_scans_packed_and_pointxyz_stride_agree(gpu_matcher):
+    wl = synth.config_corridor(n_pairs=3, n_beams=361, seed=4)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    p = Params.defaults(cov_mode=COV_CENSI_CORR)
+    gpu_matcher.upload_scans(pts, off)
+    a = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+    xyz = np.zeros((pts.shape[0], 4), np.float32)       # pcl::PointXYZ layout {x, y, z, pad}
+    xyz[:, :2] = pts
+    xyz[:, 2] = 0.0
+    xyz[:, 3] = 1.0
+    gpu_matcher.upload_scans(xyz, off)
+    b = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+    assert a.tobytes() == b.tobytes()
+    ref, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, p, fast=1)
+    assert_records_match(a, ref, "stride")
+
+
+# ---- correspondences: bit-exact index sets at equal iterate ------------------------------------------------
+@pytest.mark.parametrize("search", [SEARCH_BRUTE, SEARCH_PRUNED])
+@pytest.mark.parametrize("reciprocal", [1, 0])
+def test_correspondence_sets_bit_exact_at_every_iterate(gpu_matcher, search, reciprocal):
+    wl = synth.config_loop_closure(n_pairs=3, n_scans=16, seed=33)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    p = Params.defaults(downsample_divisor=1, search=search, use_reciprocal=reciprocal, max_iterations=40)
+    for k in range(wl.n_pairs):
+        s, t = wl.src_idx[k], wl.tgt_idx[k]
+        src, tgt = pts[off[s]:off[s + 1]], pts[off[t]:off[t + 1]]
+        _, iterates, n_corr = O.icp(src, tgt, wl.guess[k], p, trace=True)
+        # the oracle's iterate k is the accumulated float transform; replaying it from the original cloud is
+        # the same iterate for both sides (they are fed the identical T and identical points)
+        picks = sorted(set([0, 1, 2, len(iterates) // 2, len(iterates) - 1]))
+        for it in picks:
+            T = iterates[it]
+            cur = O.transform_points(T, src)
+            kk, want, want_d2 = O.correspondences(cur, tgt, p)
+            got, got_d2 = gpu_matcher.correspondences(src, tgt, T, p)
+            assert np.array_equal(got, want), (k, it)
+            m = want >= 0
+            assert np.array_equal(got_d2[m].view(np.uint32), want_d2[m].view(np.uint32)), (k, it)
+            assert int((got >= 0).sum()) == kk
+
+
+def test_correspondence_ties_pick_lowest_index(gpu_matcher):
+    # lattice target: many exact distance ties; source points on cell centres and edges
+    gx, gy = np.meshgrid(np.arange(12, dtype=np.float32) * 0.25, np.arange(9, dtype=np.float32) * 0.25)
+    tgt = np.stack([gx.ravel(), gy.ravel()], 1).astype(np.float32)
+    sx, sy = np.meshgrid(np.arange(23, dtype=np.float32) * 0.125, np.arange(17, dtype=np.float32) * 0.125)
+    src = np.stack([sx.ravel(), sy.ravel()], 1).astype(np.float32)
+    T = np.array([1, 0, 0, 0], np.float32)
+    for search in (SEARCH_BRUTE, SEARCH_PRUNED):
+        for rec in (0, 1):
+            p = Params.defaults(search=search, use_reciprocal=rec)
+            kk, want, want_d2 = O.correspondences(src, tgt, p)
+            got, got_d2 = gpu_matcher.correspondences(src, tgt, T, p)
+            assert np.array_equal(got, want), (search, rec)
+
+
+# ---- whole path: BASELINE configs at oracle-sized batches ---------------------------------------------------
+def test_config1_room_pair_default_params(gpu_matcher):
+    wl = synth.config_room_pair()
+    for p in (Params.defaults(), Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR)):
+        got, ref, _, _ = run_both(gpu_matcher, wl, p)
+        assert_records_match(got, ref, "room pair")
+        assert got["status"][0] & FLAG_CONVERGED
+        assert abs(got["tx"][0] - 0.30) < 0.02 and abs(got["ty"][0] + 0.20) < 0.02 and abs(got["theta"][0] - 0.10) < 0.01
+
+
+@pytest.mark.parametrize("search", [SEARCH_BRUTE, SEARCH_PRUNED])
+@pytest.mark.parametrize("divisor", [1, 5])
+@pytest.mark.parametrize("cov_mode", [COV_REFERENCE_LIVE, COV_CENSI_INDEXPAIR, COV_CENSI_CORR])
+def test_config2_corridor_batch(gpu_matcher, search, divisor, cov_mode):
+    wl = synth.config_corridor(n_pairs=64, seed=2)
+    p = Params.defaults(downsample_divisor=divisor, search=search, cov_mode=cov_mode)
+    got, ref, _, _ = run_both(gpu_matcher, wl, p)
+    assert_records_match(got, ref, f"corridor s{search} d{divisor} c{cov_mode}")
+    if cov_mode == COV_REFERENCE_LIVE:          # cov.h:572-575, bit-exact
+        want = np.diag([0.5, 0.5, np.float64(np.float32(0.3))]).reshape(9)
+        assert np.all(got["cov"] == want)
+
+
+@pytest.mark.parametrize("cov_cap", [200, 0])
+def test_config3_loop_closure_batch(gpu_matcher, cov_cap):
+    wl = synth.config_loop_closure(n_pairs=300, n_scans=120, seed=3)
+    p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR, cov_cap=cov_cap)
+    got, ref, _, _ = run_both(gpu_matcher, wl, p)
+    assert_records_match(got, ref, "loop closure")
+    assert (got["status"] & FLAG_CONVERGED).mean() > 0.9
+
+
+def test_dense_4096_beam_scans(gpu_matcher):
+    wl = synth.config_loop_closure(n_pairs=12, n_scans=24, n_beams=4096, seed=4)
+    for div in (1, 5):
+        p = Params.defaults(downsample_divisor=div, cov_mode=COV_CENSI_CORR)
+        got, ref, _, _ = run_both(gpu_matcher, wl, p)
+        assert_records_match(got, ref, f"dense d{div}")
+
+
+def test_maximum_size_scans(gpu_matcher):
+    wl = synth.config_corridor(n_pairs=2, n_beams=_abi.MAX_POINTS, seed=6)
+    p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR, max_iterations=12)
+    got, ref, _, _ = run_both(gpu_matcher, wl, p)
+    assert_records_match(got, ref, "8192 beams")
+    with pytest.raises(DpgIcpError) as e:
+        gpu_matcher.upload_ranges(np.ones((1, _abi.MAX_POINTS + 1), np.float32), wl.scanner)
+    assert e.value.code == -7
+
+
+def test_non_reciprocal_and_iteration_limits(gpu_matcher):
+    wl = synth.config_corridor(n_pairs=24, seed=8)
+    for kw in (dict(use_reciprocal=0), dict(max_iterations=1), dict(max_iterations=7),
+               dict(max_correspondence_distance=0.15), dict(transformation_epsilon=1e-6)):
+        p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR, **kw)
+        got, ref, _, _ = run_both(gpu_matcher, wl, p)
+        assert_records_match(got, ref, str(kw))
+    assert np.all(got["iterations"] >= 1)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------
+def test_empty_ragged_and_degenerate_inputs(gpu_matcher):
+    wl = synth.config_corridor(n_pairs=8, n_beams=721, seed=12)
+    wl.ranges[2, :] = 40.0                              # scan 2: everything at max range -> empty cloud
+    wl.ranges[4, 2:] = 40.0                             # scan 4: two points only (< 3 correspondences)
+    wl.ranges[6, ::2] = 40.0                            # scan 6: half the beams dropped
+    wl.guess[7] = (60.0, 60.0, 0.0)                     # pair 7: nothing within the 0.6 m gate
+    for cov_mode in (COV_CENSI_CORR, COV_CENSI_INDEXPAIR, COV_REFERENCE_LIVE):
+        for search in (SEARCH_BRUTE, SEARCH_PRUNED):
+            p = Params.defaults(downsample_divisor=1, cov_mode=cov_mode, search=search)
+            got, ref, _, _ = run_both(gpu_matcher, wl, p)
+            assert_records_match(got, ref, f"edge c{cov_mode} s{search}")
+    # pairs touching the empty scan: flagged, not converged, guess returned (record always written)
+    touched = (wl.src_idx == 2) | (wl.tgt_idx == 2)
+    assert np.all(got["status"][touched] & FLAG_EMPTY_INPUT)
+    assert np.all((got["status"][touched] & STOP_MASK) == STOP_NO_CORRESPONDENCES)
+    assert np.all((got["status"][touched] & FLAG_CONVERGED) == 0)
+    assert (got["status"][7] & STOP_MASK) == STOP_NO_CORRESPONDENCES and got["tx"][7] == 60.0
+
+
+def test_identical_clouds_identity(gpu_matcher):
+    wl = synth.config_room_pair()
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    pts, off = gpu_matcher.download_store()
+    p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR)
+    got = gpu_matcher.submit_pairs([0], [0], [[0, 0, 0]], p)
+    assert got["iterations"][0] == 1 and got["mse"][0] == 0.0 and got["theta"][0] == 0.0
+    assert got["n_correspondences"][0] == off[1] - off[0]
+
+
+def test_error_codes(gpu_matcher):
+    wl = synth.config_room_pair()
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    p = Params.defaults()
+    for bad, code in ((dict(src=[5], tgt=[0]), -1), (dict(src=[0], tgt=[-1]), -1)):
+        with pytest.raises(DpgIcpError) as e:
+            gpu_matcher.submit_pairs(bad["src"], bad["tgt"], [[0, 0, 0]], p)
+        assert e.value.code == code
+    with pytest.raises(DpgIcpError) as e:
+        gpu_matcher.submit_pairs([1], [0], [[np.nan, 0, 0]], p)
+    assert e.value.code == -5
+    for kw in (dict(max_iterations=0), dict(downsample_divisor=0), dict(max_correspondence_distance=-1.0),
+               dict(cov_mode=7), dict(search=9), dict(metric=5)):
+        with pytest.raises(DpgIcpError) as e:
+            gpu_matcher.submit_pairs([1], [0], [[0, 0, 0]], Params.defaults(**kw))
+        assert e.value.code == -1, kw
+    pts = np.array([[0, 0], [np.inf, 1]], np.float32)
+    with pytest.raises(DpgIcpError) as e:
+        gpu_matcher.upload_scans(pts, np.array([0, 2]))
+    assert e.value.code == -5
+    with pytest.raises(DpgIcpError) as e:
+        gpu_matcher.upload_scans(np.array([[2000.0, 0]], np.float32), np.array([0, 1]))
+    assert e.value.code == -5
+    assert gpu_matcher.submit_pairs([], [], np.zeros((0, 3)), p).shape == (0,)     # empty batch is fine
+
+
+# ---- the two reference call shapes -------------------------------------------------------------------------------
+def test_run_icp_call_shape(gpu_matcher):
+    wl = synth.config_room_pair()
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    node_1, node_2 = pts[off[0]:off[1]], pts[off[1]:off[2]]
+    from dpg_slam_b200.scanmatch import relative_guess
+    guess = relative_guess([0, 0, 0], [0.35, -0.15, 0.12])
+    converged, ((tx, ty), theta), cov, rec = gpu_matcher.run_icp(node_1, node_2, guess)      # reference defaults
+    ref = O.run_pair(node_2, node_1, guess, Params.defaults())
+    assert converged == bool(ref.status & FLAG_CONVERGED)
+    assert (tx, ty, rec.iterations, rec.status) == (ref.tx, ref.ty, ref.iterations, ref.status)
+    assert abs(theta - ref.theta) <= POSE_TOL_RAD
+    assert np.array_equal(cov, np.diag([0.5, 0.5, np.float64(np.float32(0.3))]))   # live output, cov.h:572-575
+
+
+def test_calculate_icp_cov_against_compiled_reference(gpu_matcher, cov_golden):
+    """dpgicp_cov vs the golden vectors produced by the reference's own cov_func_point_to_point.h."""
+    for c in cov_golden:
+        T = c["T_colmajor"].reshape(4, 4).T
+        live = Params.defaults(cov_mode=COV_REFERENCE_LIVE, laser_x_variance=c["live_in"][0],
+                               laser_y_variance=c["live_in"][1], laser_theta_variance=c["live_in"][2])
+        cov, st = gpu_matcher.calculate_icp_cov(c["P"], c["Q"], T, live)
+        assert np.array_equal(cov, c["live_cov"]), c["name"]                      # bit-exact live output
+        if c["singular"]:
+            continue
+        cov, st = gpu_matcher.calculate_icp_cov(c["P"], c["Q"], T, live.copy(cov_mode=COV_CENSI_INDEXPAIR))
+        rel = np.abs(cov - c["cov3"]).max() / np.abs(c["cov3"]).max()
+        assert st == 0 and rel <= COV_REL_TOL, (c["name"], rel)
+        assert rel < 1e-9, (c["name"], rel)                                       # in practice: double rounding only
+
+
+def test_enumerate_pairs_matches_oracle(gpu_matcher):
+    rng = np.random.default_rng(17)
+    for n in (0, 1, 2, 3, 200, 1500):
+        xy = rng.uniform(0, 30, (n, 2)).astype(np.float32)
+        ps = (np.arange(n) // 400).astype(np.int32)
+        src, tgt = gpu_matcher.enumerate_pairs(xy, ps, 5.0, 2.0)
+        wsrc, wtgt = O.enumerate_pairs(xy, ps, 5.0, 2.0)
+        assert np.array_equal(src, wsrc) and np.array_equal(tgt, wtgt), n
+
+
+# ---- size-independent properties at full batch sizes ------------------------------------------------------------
+def test_full_size_batch_properties(gpu_matcher):
+    """BASELINE config 2 at full size (5000 pairs, 1081 beams): the oracle checks a strided sample; the
+    whole batch is checked through properties: brute == pruned, batch == one-at-a-time, permutation
+    invariance, SPD covariances, truth recovered."""
+    wl = synth.config_corridor(n_pairs=5000, seed=2)
+    p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR)
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    got = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+    # (1) oracle on a strided sample
+    pts, off = gpu_matcher.download_store()
+    idx = np.arange(0, 5000, 97)
+    ref, _ = O.run_batch(pts, off, wl.src_idx[idx], wl.tgt_idx[idx], wl.guess[idx], p, fast=1, threads=0)
+    assert_records_match(got[idx], ref, "config2 sample")
+    # (2) exhaustive search gives the same bits as the pruned search
+    brute = gpu_matcher.submit_pairs(wl.src_idx[:600], wl.tgt_idx[:600], wl.guess[:600], p.copy(search=SEARCH_BRUTE))
+    assert brute.tobytes() == got[:600].tobytes()
+    # (3) permutation invariance / no cross-pair state
+    perm = np.random.default_rng(0).permutation(5000)
+    shuf = gpu_matcher.submit_pairs(wl.src_idx[perm], wl.tgt_idx[perm], wl.guess[perm], p)
+    assert shuf.tobytes() == got[perm].tobytes()
+    # (4) one-at-a-time equals the batch
+    for k in (0, 1234, 4999):
+        one = gpu_matcher.submit_pairs(wl.src_idx[k:k + 1], wl.tgt_idx[k:k + 1], wl.guess[k:k + 1], p)
+        assert one.tobytes() == got[k:k + 1].tobytes()
+    # (5) covariances symmetric positive definite where not flagged
+    ok = (got["status"] & FLAG_COV_SINGULAR) == 0
+    covs = got["cov"][ok].reshape(-1, 3, 3)
+    assert np.allclose(covs, covs.transpose(0, 2, 1), rtol=1e-9, atol=1e-18)
+    assert np.all(np.linalg.eigvalsh(0.5 * (covs + covs.transpose(0, 2, 1))) > 0)
+    # (6) rotation and lateral offset recovered (the corridor axis is weakly observable)
+    conv = (got["status"] & FLAG_CONVERGED) != 0
+    assert conv.mean() > 0.99
+    assert np.median(np.abs(got["theta"] - wl.truth[:, 2])) < 5e-3
+    assert np.median(np.abs(got["ty"] - wl.truth[:, 1])) < 2e-2
+
+
+def test_rotation_entries_stay_orthonormal(gpu_matcher):
+    wl = synth.config_loop_closure(n_pairs=2000, n_scans=400, seed=13)
+    p = Params.defaults(downsample_divisor=5)
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    got = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+    n = got["rot_c"].astype(np.float64) ** 2 + got["rot_s"].astype(np.float64) ** 2
+    assert np.max(np.abs(n - 1.0)) < 1e-4                # float composition over <= 500 steps
+    assert np.all(np.abs(np.arctan2(got["rot_s"], got["rot_c"]) - got["theta"]) <= POSE_TOL_RAD)
+
+
+def test_stream_and_resident_api(gpu_matcher):
+    import torch
+    wl = synth.config_corridor(n_pairs=40, n_beams=541, seed=19)
+    p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR)
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    want = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+    s = torch.cuda.Stream()
+    gpu_matcher.set_stream(s.cuda_stream)
+    try:
+        gpu_matcher.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        gpu_matcher.run(p)
+        e1.record(s)
+        got = gpu_matcher.fetch_results()
+        assert e0.elapsed_time(e1) > 0
+        assert got.tobytes() == want.tobytes()
+        c = gpu_matcher.last_run_counters()
+        assert c["iterations"] == int(got["iterations"].sum()) and c["distance_evals"] > 0
+        ptr, n = gpu_matcher.results_device_ptr()
+        assert ptr != 0 and n == 40
+    finally:
+        gpu_matcher.set_stream(None)

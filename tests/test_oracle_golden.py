@@ -1,0 +1,224 @@
+"""CPU: the oracle (oracle/dpg_oracle.c) against the golden vectors produced from the reference's
+own compiled code (tools/make_golden.py -> tests/golden/), SURVEY.md Appendix B known answers and
+analytic properties.  This is what pins the oracle before the GPU parity tests trust it."""
+import os
+
+import numpy as np
+import pytest
+
+from dpg_slam_b200 import synth
+from dpg_slam_b200._abi import (COV_CENSI_CORR, COV_CENSI_INDEXPAIR, COV_REFERENCE_LIVE, FLAG_CONVERGED,
+                                FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT, STOP_ITERATIONS, STOP_MASK,
+                                STOP_NO_CORRESPONDENCES, Params)
+from oracle import oracle_py as O
+
+
+def T_from_colmajor(Tc):
+    return np.array([Tc[0], Tc[1], Tc[12], Tc[13]], np.float32)      # T(0,0), T(1,0), T(0,3), T(1,3)
+
+
+# ---- covariance: pinned against cov_func_point_to_point.h compiled from /root/reference ----------------
+def test_cov_matches_compiled_reference(cov_golden):
+    for c in cov_golden:
+        n_h = c["P"].shape[0]
+        st, cov, H = O.cov_censi(c["P"], c["Q"][:n_h], n_h, c["n_d_used"], T_from_colmajor(c["T_colmajor"]),
+                                 sensor_var=c["sensor_var"], live=c["live_in"])
+        # Hessian restricted to (x, y, yaw): reference d2J_dX2 rows/cols (0,1,3), cov.h:90-160
+        assert np.allclose(H, c["H3"], rtol=1e-12, atol=1e-9), c["name"]
+        if c["singular"]:
+            continue                     # the reference's 6x6 is singular here (z/pitch/roll block), 3x3 may not be
+        assert st == 0, c["name"]
+        rel = np.abs(cov - c["cov3"]).max() / np.abs(c["cov3"]).max()
+        assert rel < 1e-9, (c["name"], rel)
+
+
+def test_cov_live_output_is_the_constant_diagonal(cov_golden):
+    # cov.h:572-575: the reference's live output is diag(sx2, sy2, st2) whatever the inputs
+    for c in cov_golden:
+        want = np.diag(np.array(c["live_in"], np.float32).astype(np.float64))
+        assert np.array_equal(c["live_cov"], want), c["name"]
+        p = Params.defaults(cov_mode=COV_REFERENCE_LIVE, laser_x_variance=c["live_in"][0],
+                            laser_y_variance=c["live_in"][1], laser_theta_variance=c["live_in"][2])
+        res = O.run_pair(c["P"], c["Q"], [0, 0, 0], p)
+        assert np.array_equal(np.array(res.cov).reshape(3, 3), want)
+
+
+def test_cov_kat1_survey_appendix_b():
+    P = np.array([(1.0, 0.5), (2.0, -1.0), (3.5, 0.25), (0.5, 2.0), (-1.0, 1.5)], np.float32)
+    Q = np.array([(1.2550874948501587, 0.3773355185985565), (2.3748416900634766, -0.9903373122215271),
+                  (3.7775561809539795, 0.4081680178642273), (0.5928352475166321, 1.8299250602722168),
+                  (-0.8447542786598206, 1.2076728343963623)], np.float32)
+    th = np.float32(0.1)
+    T = np.array([np.cos(np.float64(th)), np.sin(np.float64(th)), 0.3, -0.2], np.float32)
+    st, cov, H = O.cov_censi(P, Q, 5, 5, T)
+    assert st == 0
+    assert np.allclose(H, [[10, 0, -7.665528090894], [0, 10, 11.291132763709],
+                           [-7.665528090894, 11.291132763709, 52.197628147121]], atol=1e-9)
+    assert np.allclose(cov, [[0.004699660395, -0.001029669124, 0.000912736075],
+                             [-0.001029669124, 0.005515331835, -0.001343246184],
+                             [0.000912736075, -0.001343246184, 0.001190702161]], atol=1e-12)
+
+
+def test_cov_cap_quirk_h_over_all_d_over_first_200(cov_golden):
+    c = next(c for c in cov_golden if c["name"] == "kat2_cap200")
+    T = T_from_colmajor(c["T_colmajor"])
+    _, capped, _ = O.cov_censi(c["P"], c["Q"], 300, 200, T)
+    _, uncapped, _ = O.cov_censi(c["P"], c["Q"], 300, 300, T)
+    assert np.abs(capped - c["cov3"]).max() / np.abs(c["cov3"]).max() < 1e-9
+    assert np.allclose(uncapped[0, 0], 6.687777482667e-05, rtol=1e-9)       # SURVEY.md KAT-2 without the cap
+    assert not np.allclose(capped, uncapped, rtol=1e-3)
+
+
+def test_cov_singular_falls_back_to_live_diag():
+    P = np.zeros((4, 2), np.float32)
+    st, cov, _ = O.cov_censi(P, P, 4, 4, [1, 0, 0, 0])
+    assert st == FLAG_COV_SINGULAR
+    assert np.array_equal(cov, np.diag([0.5, 0.5, np.float64(np.float32(0.3))]))
+
+
+# ---- guess construction: pinned against math_utils.cc compiled from /root/reference ---------------------
+def test_angle_mod_bit_exact(math_golden):
+    got = np.array([O.angle_mod(float(a)) for a in math_golden["angle_in"]], np.float32)
+    assert np.array_equal(got.view(np.uint32), math_golden["angle_out"].view(np.uint32))
+
+
+def test_relative_guess_bit_exact(math_golden):
+    # runIcp builds the guess with inverseTransformPoint(node_2 pose, node_1 pose), dpg_slam.cc:364-368
+    for row, want in zip(math_golden["pose_pairs"], math_golden["inv_out"]):
+        g = O.relative_guess(row[0:2], float(row[2]), row[3:5], float(row[5]))
+        assert np.array_equal(g.view(np.uint32), want.view(np.uint32))
+
+
+def test_guess_matrix_entries():
+    T = O.guess_matrix([0.3, -0.2, 0.1])
+    assert T[2] == np.float32(0.3) and T[3] == np.float32(-0.2)
+    assert T[0] == np.float32(np.cos(np.float64(np.float32(0.1)))) and T[1] == np.float32(np.sin(np.float64(np.float32(0.1))))
+
+
+# ---- scan -> cloud and down-sampling (dpg_node.cc:8-26, dpg_slam.cc:346-360) ----------------------------
+def test_ranges_to_cloud_drops_max_range_and_applies_laser_offset():
+    sc = synth.Scanner(n_beams=9)
+    r = np.array([1, 30, 2, 31, 3, 29.999, 4, np.inf, 5], np.float32)
+    xy = O.ranges_to_cloud(r, sc)
+    assert xy.shape == (6, 2)                                   # 30, 31, inf dropped (range >= range_max)
+    inc = np.float32((np.float64(np.float32(sc.angle_max) - np.float32(sc.angle_min))) / 8.0)
+    kept = [0, 2, 4, 5, 6, 8]
+    for k, i in enumerate(kept):
+        a = np.float32(inc * np.float32(i) + np.float32(sc.angle_min))
+        want = (np.float32(0.2) + np.float32(np.float64(r[i]) * np.cos(np.float64(a))),
+                np.float32(0.0) + np.float32(np.float64(r[i]) * np.sin(np.float64(a))))
+        assert xy[k, 0] == want[0] and xy[k, 1] == want[1]
+
+
+def test_downsample_keeps_every_dth_compacted_index():
+    xy = np.arange(46, dtype=np.float32).reshape(23, 2)
+    assert np.array_equal(O.downsample(xy, 5), xy[::5])
+    assert np.array_equal(O.downsample(xy, 1), xy)
+    assert O.downsample(xy[:0], 5).shape == (0, 2)
+
+
+# ---- ICP loop (PCL semantics restated; parity UNPINNED, properties only) ----------
+def _room_pair(seed=1):
+    wl = synth.config_room_pair(seed=seed)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    return wl, pts[off[0]:off[1]], pts[off[1]:off[2]]
+
+
+def test_icp_recovers_known_offset_noise_free():
+    sc = synth.Scanner(noise_sigma=0.0)
+    poses = np.array([[0.0, 0.0, 0.0], [0.30, -0.20, 0.10]])
+    ranges = synth.cast_scans(synth.world_room(), poses, sc, 1)
+    tgt, src = O.ranges_to_cloud(ranges[0], sc), O.ranges_to_cloud(ranges[1], sc)
+    p = Params.defaults(downsample_divisor=1)
+    res = O.run_pair(src, tgt, [0.35, -0.15, 0.12], p)
+    assert res.status & FLAG_CONVERGED
+    # sampling differs between the two scans, so ICP recovers the offset to a few mm, not 1e-6
+    assert abs(res.tx - 0.30) < 5e-3 and abs(res.ty + 0.20) < 5e-3 and abs(res.theta - 0.10) < 2e-3
+
+
+def test_icp_identical_clouds_converges_to_identity_in_one_step():
+    _, tgt, _ = _room_pair()
+    p = Params.defaults(downsample_divisor=1)
+    res = O.run_pair(tgt, tgt, [0, 0, 0], p)
+    assert res.iterations == 1 and res.mse == 0.0 and res.n_correspondences == len(tgt)
+    assert (res.tx, res.ty, res.theta) == (0.0, 0.0, 0.0) and res.status & FLAG_CONVERGED
+
+
+def test_grid_search_equals_brute_force():
+    wl = synth.config_corridor(n_pairs=6, seed=11)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    for div in (1, 5):
+        p = Params.defaults(downsample_divisor=div, cov_mode=COV_CENSI_CORR)
+        a, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, p, fast=0)
+        b, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, p, fast=1)
+        assert a.tobytes() == b.tobytes()
+
+
+def test_correspondences_reciprocal_gate_and_ties():
+    # target points on a lattice: source point exactly between two targets -> lowest index wins
+    tgt = np.array([(0, 0), (1, 0), (2, 0), (10, 10)], np.float32)
+    src = np.array([(0.5, 0), (2.1, 0), (5, 5), (0.4, 0.0)], np.float32)
+    p = Params.defaults()
+    k, corr, d2 = O.correspondences(src, tgt, p.copy(use_reciprocal=0))
+    assert list(corr) == [0, 2, -1, 0] and k == 3                 # tie at 0.5 -> index 0; (5,5) beyond 0.6 m
+    k, corr, _ = O.correspondences(src, tgt, p)
+    assert list(corr) == [-1, 2, -1, 0] and k == 2                # target 0 prefers source 3 (0.4 < 0.5)
+    assert d2[0] == np.float32(0.25)
+    # gate is <=: a distance of exactly floor32(0.36) passes
+    thr = np.float32(0.36) if np.float64(np.float32(0.36)) <= 0.6 * 0.6 else np.nextafter(np.float32(0.36), np.float32(0))
+    src2 = np.array([(np.sqrt(np.float64(thr)), 0)], np.float32)
+    if np.float32(src2[0, 0] * src2[0, 0]) <= thr:
+        k, corr, _ = O.correspondences(src2, tgt[:1], p.copy(use_reciprocal=0))
+        assert k == 1
+
+
+def test_icp_stop_reasons_and_flags():
+    _, tgt, src = _room_pair()
+    p = Params.defaults(downsample_divisor=1)
+    far = O.run_pair(src, tgt, [50, 50, 0], p)                    # nothing within 0.6 m
+    assert far.status & STOP_MASK == STOP_NO_CORRESPONDENCES and not far.status & FLAG_CONVERGED
+    assert far.iterations == 0 and far.tx == 50 and far.ty == 50  # the guess is returned, record always written
+    one = O.run_pair(src, tgt, [0.35, -0.15, 0.12], p.copy(max_iterations=1))
+    assert one.status & STOP_MASK == STOP_ITERATIONS and one.status & FLAG_CONVERGED and one.iterations == 1
+    empty = O.run_pair(src[:0], tgt, [0, 0, 0], p)
+    assert empty.status & FLAG_EMPTY_INPUT and empty.status & STOP_MASK == STOP_NO_CORRESPONDENCES
+    two = O.run_pair(src[:2], tgt, [0.3, -0.2, 0.1], p)
+    assert two.status & STOP_MASK == STOP_NO_CORRESPONDENCES      # < 3 correspondences (PCL min_number_correspondences_)
+
+
+def test_censi_corr_covariance_is_spd_and_small():
+    wl = synth.config_loop_closure(n_pairs=12, n_scans=40, seed=5)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR)
+    res, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, p, fast=1)
+    ok = (res["status"] & FLAG_COV_SINGULAR) == 0
+    assert ok.sum() >= 8
+    for c in res["cov"][ok]:
+        c = c.reshape(3, 3)
+        assert np.allclose(c, c.T, rtol=1e-9, atol=1e-18)
+        assert np.all(np.linalg.eigvalsh(0.5 * (c + c.T)) > 0)
+
+
+def test_indexpair_mode_uses_full_clouds_and_shorter_length():
+    wl, tgt, src = _room_pair()
+    p = Params.defaults(cov_mode=COV_CENSI_INDEXPAIR)             # divisor 5 for ICP, FULL clouds for the covariance
+    res = O.run_pair(src, tgt[:-7], wl.guess[0], p)
+    nh = min(len(src), len(tgt) - 7)
+    T = [res.rot_c, res.rot_s, res.tx, res.ty]
+    _, want, _ = O.cov_censi(src, tgt[:-7], nh, 200, T)
+    assert np.array_equal(np.array(res.cov).reshape(3, 3), want)
+
+
+def test_enumerate_pairs_matches_reference_loop_order():
+    rng = np.random.default_rng(3)
+    xy = rng.uniform(0, 12, (60, 2)).astype(np.float32)
+    ps = (np.arange(60) // 25).astype(np.int32)
+    src, tgt = O.enumerate_pairs(xy, ps, 5.0, 2.0)
+    want = []
+    for i in range(1, 60):                                        # dpg_slam.cc:79-107
+        want.append((i, i - 1))
+        for j in range(0, i - 1):
+            d = np.sqrt(np.float32(np.float32((xy[j, 0] - xy[i, 0]) ** 2) + np.float32((xy[j, 1] - xy[i, 1]) ** 2)))
+            if d <= (5.0 if ps[j] == ps[i] else 2.0):
+                want.append((i, j))
+    assert list(zip(src.tolist(), tgt.tolist())) == want
