@@ -468,8 +468,9 @@ int dpgicp_run(dpgicp_ctx *ctx, const dpgicp_params *params) {
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   int rc = check_params(ctx, params);
   if (rc) return rc;
+  if (ctx->batch.n_pairs == 0) return DPGICP_OK;               /* an empty batch is valid and does nothing */
+  if (ctx->batch.n_pairs < 0) return fail(ctx, DPGICP_E_STATE, "no pair list set");
   if (ctx->store.n_scans <= 0) return fail(ctx, DPGICP_E_STATE, "no scans uploaded");
-  if (ctx->batch.n_pairs <= 0) return ctx->batch.n_pairs == 0 ? DPGICP_OK : DPGICP_E_STATE;
   return launch_icp(ctx, ctx->store, ctx->batch, params, nullptr, nullptr);
 }
 

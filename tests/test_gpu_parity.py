@@ -230,7 +230,10 @@ def test_error_codes(gpu_matcher):
     with pytest.raises(DpgIcpError) as e:
         gpu_matcher.upload_scans(np.array([[2000.0, 0]], np.float32), np.array([0, 1]))
     assert e.value.code == -5
-    assert gpu_matcher.submit_pairs([], [], np.zeros((0, 3)), p).shape == (0,)     # empty batch is fine
+    assert gpu_matcher.submit_pairs([], [], np.zeros((0, 3)), p).shape == (0,)     # empty batch is fine, even with no store
+    with pytest.raises(DpgIcpError) as e:                                          # a failed upload leaves no store behind
+        gpu_matcher.submit_pairs([0], [0], [[0, 0, 0]], p)
+    assert e.value.code == -6
 
 
 # ---- the two reference call shapes -------------------------------------------------------------------------------
