@@ -104,7 +104,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libdpgicp.so")
+    # DPGICP_LIBRARY selects a development build variant of the same library (A/B timing)
+    return os.environ.get("DPGICP_LIBRARY") or os.path.join(_HERE, "libdpgicp.so")
 
 
 def load_library() -> C.CDLL:

@@ -53,7 +53,9 @@ struct dpgicp_ctx {
   Store store, scratch_store;
   Batch batch, scratch_batch;
   DevBuf stage, offsets, misc, corr;
-  unsigned long long *d_queue = nullptr;     /* [0] queue head, [8..15] counters */
+  DevBuf state[2], susp[2];                  /* suspended-pair state slots + pair lists, ping-pong between stages */
+  unsigned long long *d_queue = nullptr;     /* [0..2] stage queue heads, [4],[5] suspended counts, [8..15] counters */
+  int max_stages = 3;
   int *d_bad = nullptr;
   int force_warps = 0;
   int force_ctas_per_sm = 0;
@@ -118,17 +120,21 @@ float gate_threshold(const dpgicp_params *p) {
 }
 
 template <int WARPS, bool PRUNED>
-int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t n_pairs) {
+int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t max_items, int *grid_out) {
   auto kern = icp_pairs_kernel<WARPS, PRUNED>;
   CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
   if (per_sm < 1) return fail(ctx, DPGICP_E_TOOBIG, "scan too large for one CTA's shared memory");
   if (ctx->force_ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->force_ctas_per_sm);
-  /* persistent grid: a whole number of resident CTAs per SM, never more CTAs than pairs */
+  /* persistent grid: a whole number of resident CTAs per SM, never more CTAs than work items */
   int64_t grid = (int64_t)ctx->sm_count * per_sm;
-  if (grid > n_pairs) grid = n_pairs;
+  if (grid > max_items) grid = max_items;
   if (grid < 1) grid = 1;
+  if (grid_out) {
+    if (*grid_out < 0) { *grid_out = (int)grid; return DPGICP_OK; }      /* query only */
+    *grid_out = (int)grid;
+  }
   kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(kp);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
@@ -136,21 +142,25 @@ int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t n
 }
 
 template <bool PRUNED>
-int launch_icp_w(dpgicp_ctx *ctx, int warps, const KernelParams &kp, size_t smem, int64_t n) {
+int launch_icp_w(dpgicp_ctx *ctx, int warps, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
   switch (warps) {
-    case 1: return launch_icp_t<1, PRUNED>(ctx, kp, smem, n);
-    case 2: return launch_icp_t<2, PRUNED>(ctx, kp, smem, n);
-    case 4: return launch_icp_t<4, PRUNED>(ctx, kp, smem, n);
-    case 8: return launch_icp_t<8, PRUNED>(ctx, kp, smem, n);
-    default: return launch_icp_t<16, PRUNED>(ctx, kp, smem, n);
+    case 1: return launch_icp_t<1, PRUNED>(ctx, kp, smem, n, grid_out);
+    case 2: return launch_icp_t<2, PRUNED>(ctx, kp, smem, n, grid_out);
+    case 4: return launch_icp_t<4, PRUNED>(ctx, kp, smem, n, grid_out);
+    case 8: return launch_icp_t<8, PRUNED>(ctx, kp, smem, n, grid_out);
+    default: return launch_icp_t<16, PRUNED>(ctx, kp, smem, n, grid_out);
   }
+}
+
+int launch_stage(dpgicp_ctx *ctx, bool pruned, int warps, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
+  return pruned ? launch_icp_w<true>(ctx, warps, kp, smem, n, grid_out) : launch_icp_w<false>(ctx, warps, kp, smem, n, grid_out);
 }
 
 int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_params *p, int32_t *corr_out,
                float *corr_d2) {
   const int div = p->downsample_divisor;
   int n_max = (st.max_count + div - 1) / div;
-  int n_cap = ((std::max(n_max, 1) + kGroup - 1) / kGroup) * kGroup;
+  int n_cap = ((std::max(n_max, 1) + kTile - 1) / kTile) * kTile;
   if (n_cap > DPGICP_MAX_POINTS) return fail(ctx, DPGICP_E_TOOBIG, "scan exceeds DPGICP_MAX_POINTS");
   KernelParams kp;
   std::memset(&kp, 0, sizeof(kp));
@@ -160,7 +170,6 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   kp.store.n_scans = st.n_scans;
   kp.tasks = (const PairTask *)b.tasks.p;
   kp.results = (dpgicp_result *)b.results.p;
-  kp.queue = ctx->d_queue;
   kp.counters = ctx->d_queue + 8;
   kp.n_pairs = b.n_pairs;
   kp.n_cap = n_cap;
@@ -177,12 +186,60 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   kp.live[0] = p->laser_x_variance; kp.live[1] = p->laser_y_variance; kp.live[2] = p->laser_theta_variance;
   kp.corr_out = corr_out;
   kp.corr_d2_out = corr_d2;
+  kp.slot_bytes = (long long)kStateHeader + 12ll * n_cap;
   const size_t smem = smem_bytes(n_cap);
-  int warps = ctx->force_warps;
-  if (warps <= 0) warps = n_cap <= 512 ? 2 : (n_cap <= 2048 ? 4 : 8);
+  const bool pruned = p->search == DPGICP_SEARCH_PRUNED;
+
+  /* stage widths (warps per pair): narrow for the bulk, wider for the pairs still running when a
+   * stage's queue runs dry; never more warps than the pair has 32-point tiles */
+  const int tiles = n_cap / kTile;
+  int w0 = ctx->force_warps;
+  if (w0 <= 0) w0 = n_cap <= 512 ? 2 : (n_cap <= 2048 ? 4 : 8);
+  int widths[3] = {w0, w0, w0};
+  int n_stages = 1;
+  if (corr_out == nullptr) {
+    for (int k = 1; k < ctx->max_stages; ++k) {
+      int w = std::min(16, widths[n_stages - 1] * 2);
+      while (w > 1 && w > tiles) w >>= 1;
+      if (w <= widths[n_stages - 1]) break;
+      widths[n_stages++] = w;
+    }
+  }
   CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, 16 * sizeof(unsigned long long), ctx->stream));
-  if (p->search == DPGICP_SEARCH_PRUNED) return launch_icp_w<true>(ctx, warps, kp, smem, b.n_pairs);
-  return launch_icp_w<false>(ctx, warps, kp, smem, b.n_pairs);
+  int grid_prev = 0;
+  if (n_stages > 1) {
+    /* every stage can suspend at most one pair per CTA: size the state slots for stage 0's grid */
+    int g0 = -1;
+    int rc = launch_stage(ctx, pruned, widths[0], kp, smem, b.n_pairs, &g0);
+    if (rc) return rc;
+    for (int k = 0; k < 2; ++k) {
+      if ((rc = reserve(ctx, ctx->state[k], (size_t)g0 * (size_t)kp.slot_bytes))) return rc;
+      if ((rc = reserve(ctx, ctx->susp[k], (size_t)g0 * sizeof(long long)))) return rc;
+    }
+  }
+  for (int sidx = 0; sidx < n_stages; ++sidx) {
+    KernelParams ks = kp;
+    ks.queue = ctx->d_queue + sidx;
+    ks.resume = sidx > 0 ? 1 : 0;
+    if (sidx > 0) {
+      ks.in_count = reinterpret_cast<const unsigned int *>(ctx->d_queue + 4 + ((sidx - 1) & 1));
+      ks.susp_in = (const long long *)ctx->susp[(sidx - 1) & 1].p;
+      ks.state_in = (const unsigned char *)ctx->state[(sidx - 1) & 1].p;
+    }
+    if (sidx + 1 < n_stages) {
+      ks.out_count = reinterpret_cast<unsigned int *>(ctx->d_queue + 4 + (sidx & 1));
+      ks.susp_out = (long long *)ctx->susp[sidx & 1].p;
+      ks.state_out = (unsigned char *)ctx->state[sidx & 1].p;
+      if (sidx >= 2)      /* the count cell is reused by stage sidx: clear it after stage sidx-1 consumed it */
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue + 4 + (sidx & 1), 0, sizeof(unsigned long long), ctx->stream));
+    }
+    int grid = 0;
+    const int64_t max_items = sidx == 0 ? b.n_pairs : (int64_t)grid_prev;
+    int rc = launch_stage(ctx, pruned, widths[sidx], ks, smem, max_items, &grid);
+    if (rc) return rc;
+    grid_prev = grid;
+  }
+  return DPGICP_OK;
 }
 
 int finish_store(dpgicp_ctx *ctx, Store &st, int n_scans) {
@@ -356,6 +413,7 @@ int dpgicp_create(int device, dpgicp_ctx **out) {
   }
   if (const char *w = std::getenv("DPGICP_WARPS")) ctx->force_warps = std::atoi(w);
   if (const char *c = std::getenv("DPGICP_CTAS_PER_SM")) ctx->force_ctas_per_sm = std::atoi(c);
+  if (const char *c = std::getenv("DPGICP_STAGES")) ctx->max_stages = std::max(1, std::min(3, std::atoi(c)));
   *out = ctx;
   return DPGICP_OK;
 }
@@ -370,6 +428,7 @@ void dpgicp_destroy(dpgicp_ctx *ctx) {
     if (b->h_tasks) cudaFreeHost(b->h_tasks);
   }
   release(ctx->stage); release(ctx->offsets); release(ctx->misc); release(ctx->corr);
+  for (int k = 0; k < 2; ++k) { release(ctx->state[k]); release(ctx->susp[k]); }
   if (ctx->d_queue) cudaFree(ctx->d_queue);
   if (ctx->d_bad) cudaFree(ctx->d_bad);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -33,11 +33,18 @@
 
 namespace dpg {
 
-constexpr int   kGroup = 32;        /* points per bounding-box group = lanes per warp            */
+#ifndef DPGICP_GROUP
+#define DPGICP_GROUP 16
+#endif
+constexpr int   kTile  = 32;            /* queries per warp (one per lane)                            */
+constexpr int   kGroup = DPGICP_GROUP;  /* points per bounding-box group of a searched cloud          */
+static_assert(kGroup == 8 || kGroup == 16 || kGroup == 32, "kGroup must be 8, 16 or 32");
 constexpr float kPad   = 1.0e30f;   /* coordinate of padded slots: any d2 against it is +inf      */
 constexpr double kScaleLin  = 4294967296.0;      /* 2^32 */
 constexpr double kScaleProd = 268435456.0;       /* 2^28 */
 constexpr double kScaleD2   = 1099511627776.0;   /* 2^40 */
+constexpr int   kMaxWarps = 16;
+constexpr int   kStateHeader = 64;  /* bytes of scalars in front of a suspended pair's arrays      */
 
 struct PairTask {            /* 24 bytes: pair indices + the guess as matrix entries (host libm) */
   int32_t src, tgt;
@@ -51,11 +58,21 @@ struct StoreView {           /* scan store: padded rows of float2, beam order, M
   int32_t n_scans;
 };
 
+/* scalars of a suspended pair (first kStateHeader bytes of its state slot) */
+struct SuspHeader {
+  float fc, fs, ftx, fty;
+  double mse, mse_prev;
+  int32_t iterations, last_k;
+  uint32_t status;
+  int32_t pad;
+};
+static_assert(sizeof(SuspHeader) <= kStateHeader, "state header too small");
+
 struct KernelParams {
   StoreView store;
   const PairTask *tasks;
   dpgicp_result *results;
-  unsigned long long *queue;      /* work-queue head                                              */
+  unsigned long long *queue;      /* work-queue head of THIS stage                                */
   unsigned long long *counters;   /* [0] iterations [1] correspondences [2] distance evals [3] box tests */
   long long n_pairs;
   int32_t n_cap;                  /* smem capacity per cloud in points, multiple of 32            */
@@ -66,6 +83,16 @@ struct KernelParams {
   /* dpgicp_correspondences hook: when corr_out != nullptr the kernel runs ONE pass for pair 0    */
   int32_t *corr_out;
   float *corr_d2_out;
+  /* staged execution (see icp_pairs_kernel): work items of stage > 0 are the pairs the previous
+   * stage suspended when its queue ran dry; they are resumed by wider CTAs                        */
+  int32_t resume;                     /* 0: items are fresh tasks; 1: items are susp_in[0..*in_count) */
+  const unsigned int *in_count;
+  const long long *susp_in;           /* pair index per suspended item; item k's state is slot k   */
+  const unsigned char *state_in;
+  unsigned int *out_count;            /* nullptr: final stage, never suspends                      */
+  long long *susp_out;
+  unsigned char *state_out;
+  long long slot_bytes;               /* kStateHeader + 12 * n_cap                                 */
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -162,35 +189,37 @@ struct SmemLayout {
   float2 *tgt;      /* n_cap */
   float2 *src;      /* n_cap, current (incrementally transformed) source                           */
   int32_t *nn;      /* n_cap, forward neighbour of the previous pass (seed) / final correspondences */
-  float4 *tbox;     /* n_cap/32 */
-  float4 *sbox;     /* n_cap/32 */
+  float4 *tbox;     /* n_cap/kGroup group boxes of the target                                        */
+  float4 *sbox;     /* n_cap/kGroup group boxes of the current source                                */
+  float4 *stile;    /* n_cap/32 boxes of the source tiles (query boxes of the forward search)        */
   int32_t *tcnt;    /* n_cap/32 accepted per source tile (rank for the covariance cap)              */
   long long *red;   /* 16 int64 moment sums                                                         */
   double *dpart;    /* kMaxWarps * 12 partial double sums (deterministic order)                     */
   float *step;      /* 4 */
-  int32_t *ctl;     /* [0] pair index lo [1] pair index hi [2] stop [3] K                            */
+  int32_t *ctl;     /* [0] item lo [1] item hi [2] stop [3] K [4] slot                               */
   uint64_t *mbar;
 };
-constexpr int kMaxWarps = 16;
 
 __host__ __device__ inline size_t smem_bytes(int n_cap) {
-  const int g = n_cap / kGroup;
-  return (size_t)n_cap * (8 + 8 + 4) + (size_t)g * (16 + 16 + 4) + 16 * 8 + kMaxWarps * 12 * 8 + 16 + 32 + 16 + 64;
+  const int g = n_cap / kGroup, t = n_cap / kTile;
+  return (size_t)n_cap * (8 + 8 + 4) + (size_t)g * (16 + 16) + (size_t)t * (16 + 4) + 16 * 8 + kMaxWarps * 12 * 8 + 16 + 32 +
+         16 + 64;
 }
 
 __device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap) {
-  const int g = n_cap / kGroup;
+  const int g = n_cap / kGroup, t = n_cap / kTile;
   SmemLayout L;
   size_t o = 0;
   L.tgt = (float2 *)(base + o);  o += (size_t)n_cap * 8;
   L.src = (float2 *)(base + o);  o += (size_t)n_cap * 8;
+  L.nn = (int32_t *)(base + o);  o += (size_t)n_cap * 4;      /* n_cap % 32 == 0: stays 16-byte aligned */
   L.tbox = (float4 *)(base + o); o += (size_t)g * 16;
   L.sbox = (float4 *)(base + o); o += (size_t)g * 16;
+  L.stile = (float4 *)(base + o); o += (size_t)t * 16;
   L.red = (long long *)(base + o); o += 16 * 8;
   L.dpart = (double *)(base + o);  o += kMaxWarps * 12 * 8;
   L.mbar = (uint64_t *)(base + o); o += 16;
-  L.nn = (int32_t *)(base + o);   o += (size_t)n_cap * 4;
-  L.tcnt = (int32_t *)(base + o); o += (size_t)g * 4;
+  L.tcnt = (int32_t *)(base + o); o += (size_t)t * 4;
   L.step = (float *)(base + o);   o += 16;
   L.ctl = (int32_t *)(base + o);  o += 32;
   return L;
@@ -207,19 +236,60 @@ __device__ __forceinline__ float4 warp_box(float2 p, bool valid) {
   return b;
 }
 
+/* Boxes of one tile (32 points, one per lane): the kGroup-point group boxes (every lane of a group
+ * gets its group's box) and the whole tile's box. */
+__device__ __forceinline__ void tile_boxes(float2 p, bool valid, float4 &gbox, float4 &tbox) {
+  if (kGroup == kTile) {
+    gbox = tbox = warp_box(p, valid);
+    return;
+  }
+  const float inf = __int_as_float(0x7f800000);
+  float4 b = make_float4(valid ? p.x : inf, valid ? p.y : inf, valid ? p.x : -inf, valid ? p.y : -inf);
+#pragma unroll
+  for (int o = 1; o < kGroup; o <<= 1) {
+    b.x = fminf(b.x, __shfl_xor_sync(0xffffffffu, b.x, o));
+    b.y = fminf(b.y, __shfl_xor_sync(0xffffffffu, b.y, o));
+    b.z = fmaxf(b.z, __shfl_xor_sync(0xffffffffu, b.z, o));
+    b.w = fmaxf(b.w, __shfl_xor_sync(0xffffffffu, b.w, o));
+  }
+  gbox = b;
+  tbox.x = warp_min(b.x); tbox.y = warp_min(b.y); tbox.z = warp_max(b.z); tbox.w = warp_max(b.w);
+}
+
+/* store the boxes of tile `tile` of a cloud: group boxes into gb[], tile box into tb[] (may be null) */
+__device__ __forceinline__ void store_tile_boxes(float2 p, bool valid, int tile, float4 *gb, float4 *tb) {
+  const int lane = threadIdx.x & 31;
+  float4 g, t;
+  tile_boxes(p, valid, g, t);
+  if ((lane & (kGroup - 1)) == 0) gb[tile * (kTile / kGroup) + lane / kGroup] = g;
+  if (tb != nullptr && lane == 0) tb[tile] = t;
+}
+
+/* executed-work counters kept in registers by every warp, flushed once per CTA */
+struct SearchStats {
+  unsigned scans = 0, tests = 0;
+#ifdef DPGICP_STATS
+  unsigned cands = 0, loose = 0, searches = 0;
+#endif
+};
+
 /* ------------------------------------------------------------------------------------------------
  * Exact nearest neighbour of one query per lane over a grouped cloud in shared memory.
- *   bd/bj in: current bound (gate or seed), out: (d2, index)-lexicographic minimum among points
- *   with d2 <= initial bd.  `qbox` is the bounding box of the valid lanes' queries.
- *   PRUNED = false scans every group.
+ *   (bd, bj) in: current best (the gate / a seed / for the reciprocal test the pair being tested),
+ *   out: the (d2, index)-lexicographic minimum of the input and every point of the cloud.
+ *   `qbox` is the bounding box of the active lanes' queries.  PRUNED = false scans every group.
  * ---------------------------------------------------------------------------------------------- */
 template <bool PRUNED>
 __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
-                                          int n_groups, float qx, float qy, bool valid, float4 qbox,
-                                          float &bd, int &bj, unsigned &scans, unsigned &tests) {
+                                          int n_groups, float qx, float qy, bool active, float4 qbox,
+                                          float &bd, int &bj, SearchStats &st, float gate) {
   const int lane = threadIdx.x & 31;
   float bmax = 0.0f;
-  if (PRUNED) bmax = warp_max(valid ? bd : -1.0f);
+  if (PRUNED) bmax = warp_max(active ? bd : -1.0f);
+#ifdef DPGICP_STATS
+  st.searches++;
+  if (bmax >= gate) st.loose++;
+#endif
   for (int base = 0; base < n_groups; base += 32) {
     unsigned mask;
     if (PRUNED) {
@@ -227,7 +297,10 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
       bool cand = false;
       if (g < n_groups) cand = lb_box_box(qbox, boxes[g]) <= bmax;
       mask = __ballot_sync(0xffffffffu, cand);
-      ++tests;
+      ++st.tests;
+#ifdef DPGICP_STATS
+      st.cands += __popc(mask);
+#endif
     } else {
       const int rem = n_groups - base;
       mask = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
@@ -236,11 +309,26 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
       const int g = base + __ffs(mask) - 1;
       mask &= mask - 1;
       if (PRUNED) {
-        const bool need = valid && (lb_point_box(qx, qy, boxes[g]) <= bd);
+        const bool need = active && (lb_point_box(qx, qy, boxes[g]) <= bd);
         if (!__any_sync(0xffffffffu, need)) continue;
       }
-      ++scans;
+      ++st.scans;
       const float4 *pp = reinterpret_cast<const float4 *>(cloud + g * kGroup);
+#ifdef DPGICP_DUAL_CHAIN
+      /* two independent (d2, index) chains (even / odd points) halve the dependent-compare latency;
+       * merged lexicographically, so the result is the first minimum as before */
+      float gd = __int_as_float(0x7f800000), hd = gd;
+      int gj = 0, hj = 1;
+#pragma unroll
+      for (int t = 0; t < kGroup / 2; ++t) {
+        const float4 p = pp[t];                       /* two points per LDS.128, broadcast       */
+        const float d0 = dist2(qx, qy, p.x, p.y);
+        const float d1 = dist2(qx, qy, p.z, p.w);
+        if (d0 < gd) { gd = d0; gj = 2 * t; }
+        if (d1 < hd) { hd = d1; hj = 2 * t + 1; }
+      }
+      if (hd < gd || (hd == gd && hj < gj)) { gd = hd; gj = hj; }
+#else
       float gd = __int_as_float(0x7f800000);
       int gj = 0;
 #pragma unroll
@@ -251,73 +339,25 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
         if (d0 < gd) { gd = d0; gj = 2 * t; }
         if (d1 < gd) { gd = d1; gj = 2 * t + 1; }
       }
+#endif
       const int j = g * kGroup + gj;
       if (gd < bd || (gd == bd && j < bj)) { bd = gd; bj = j; }
     }
   }
 }
 
-/* Is there a point i' in the grouped cloud with (d2(i', r), i') < (bd, self) lexicographically?
- * (reciprocity test of PCL's determineReciprocalCorrespondences: the query r = tgt[j] must have the
- * source point `self` as ITS nearest neighbour.) */
-template <bool PRUNED>
-__device__ __forceinline__ bool beaten_search(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
-                                              int n_groups, float rx, float ry, bool active, float4 rbox,
-                                              float bd, int self, unsigned &scans, unsigned &tests) {
-  const int lane = threadIdx.x & 31;
-  bool beaten = false;
-  float bmax = 0.0f;
-  if (PRUNED) bmax = warp_max(active ? bd : -1.0f);
-  for (int base = 0; base < n_groups; base += 32) {
-    unsigned mask;
-    if (PRUNED) {
-      const int g = base + lane;
-      bool cand = false;
-      if (g < n_groups) cand = lb_box_box(rbox, boxes[g]) <= bmax;
-      mask = __ballot_sync(0xffffffffu, cand);
-      ++tests;
-    } else {
-      const int rem = n_groups - base;
-      mask = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-    }
-    while (mask) {
-      const int g = base + __ffs(mask) - 1;
-      mask &= mask - 1;
-      if (PRUNED) {
-        const bool need = active && !beaten && (lb_point_box(rx, ry, boxes[g]) <= bd);
-        if (!__any_sync(0xffffffffu, need)) continue;
-      }
-      ++scans;
-      const float4 *pp = reinterpret_cast<const float4 *>(cloud + g * kGroup);
-      /* lowest distance in the group and the first index attaining it */
-      float gd = __int_as_float(0x7f800000);
-      int gj = 0;
-#pragma unroll
-      for (int t = 0; t < kGroup / 2; ++t) {
-        const float4 p = pp[t];
-        const float d0 = dist2(p.x, p.y, rx, ry);
-        const float d1 = dist2(p.z, p.w, rx, ry);
-        if (d0 < gd) { gd = d0; gj = 2 * t; }
-        if (d1 < gd) { gd = d1; gj = 2 * t + 1; }
-      }
-      const int i2 = g * kGroup + gj;
-      if (gd < bd || (gd == bd && i2 < self)) beaten = true;
-    }
-  }
-  return beaten;
-}
-
 /* ------------------------------------------------------------------------------------------------
  * One correspondence pass for one source tile (32 consecutive source points, one per lane).
- * Returns accept flag; j = matched target index, d = its squared distance.  Updates the seed.
+ * Returns accept flag; j = matched target index, d = its squared distance.
+ * PCL determineReciprocalCorrespondences (App. A.3-2): forward NN within the gate, then the target
+ * point's own nearest source point must be the query ((d2, index)-lexicographic, like the forward).
  * ---------------------------------------------------------------------------------------------- */
 template <bool PRUNED>
 __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns, int n_groups_s,
                                            int n_groups_t, float gate, bool reciprocal, float2 &q,
-                                           int &j_out, float &d_out, bool &fwd_ok, unsigned &scans,
-                                           unsigned &tests) {
+                                           int &j_out, float &d_out, bool &fwd_ok, SearchStats &st) {
   const int lane = threadIdx.x & 31;
-  const int i = tile * kGroup + lane;
+  const int i = tile * kTile + lane;
   const bool valid = i < ns;
   q = L.src[i];
   float bd = gate;
@@ -330,20 +370,20 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
       if (d0 <= gate) { bd = d0; bj = seed; }
     }
   }
-  nn_search<PRUNED>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.sbox[tile], bd, bj, scans, tests);
+  nn_search<PRUNED>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, st, gate);
   fwd_ok = valid && (bj != 0x7fffffff);
   j_out = bj;
   d_out = bd;
   bool accept = fwd_ok;
-  if (reciprocal) {
+  if (reciprocal && __any_sync(0xffffffffu, fwd_ok)) {
     float2 r = make_float2(0.f, 0.f);
     if (fwd_ok) r = L.tgt[bj];
     const float4 rbox = warp_box(r, fwd_ok);
-    if (__any_sync(0xffffffffu, fwd_ok)) {
-      const bool beaten =
-          beaten_search<PRUNED>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, bd, i, scans, tests);
-      accept = fwd_ok && !beaten;
-    }
+    float rd = bd;
+    int ri = i;
+    /* dist2(r, p) == dist2(p, r) bit for bit: fl(a-b) = -fl(b-a) and the square drops the sign */
+    nn_search<PRUNED>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, rd, ri, st, gate);
+    accept = fwd_ok && (ri == i);
   }
   return accept;
 }
@@ -424,84 +464,112 @@ __device__ __forceinline__ void block_sum11(double *acc, double *dpart, double *
 }
 
 /* ------------------------------------------------------------------------------------------------
- * the persistent ICP + covariance kernel
+ * The persistent ICP + covariance kernel.
+ *
+ * Staged execution.  ICP iteration counts are heavy-tailed (corridor workload: median 37, p99 174,
+ * max 305 passes), so a fixed CTA shape either wastes the machine on the last long pairs (narrow
+ * CTAs: few warps left running) or wastes issue slots on the bulk (wide CTAs).  The host therefore
+ * launches the same kernel as a chain of stages with growing WARPS.  A stage works through its queue;
+ * once the queue is EMPTY, every CTA suspends the pair it is on at the next pass boundary (current
+ * source cloud, neighbour seeds and a few scalars go to a state slot in HBM) and the stage ends with
+ * all SMs still busy.  The next, wider stage resumes the suspended pairs — at most one per CTA of the
+ * previous stage — with more warps per pair.  The last stage runs to completion.  State is restored
+ * bit for bit, so staging cannot change results (tested: any chain == single stage).
  * ---------------------------------------------------------------------------------------------- */
+/* resident CTAs per SM the register allocation is held to (DPGICP_TARGET_WARPS resident warps per SM) */
+#ifndef DPGICP_TARGET_WARPS
+#define DPGICP_TARGET_WARPS 24
+#endif
+__host__ __device__ constexpr int min_ctas(int warps) {
+  return (DPGICP_TARGET_WARPS / warps) < 1 ? 1 : (DPGICP_TARGET_WARPS / warps) > 16 ? 16 : (DPGICP_TARGET_WARPS / warps);
+}
+
 template <int WARPS, bool PRUNED>
-__global__ void __launch_bounds__(WARPS * 32) icp_pairs_kernel(const KernelParams P) {
+__global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(const KernelParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SmemLayout L = carve(smem_raw, P.n_cap);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int div = P.divisor;
+  constexpr int GPT = kTile / kGroup;        /* groups per tile */
   uint32_t mbar_phase = 0;
 
   if (tid == 0) mbar_init(L.mbar, 1);
   __syncthreads();
 
-  unsigned c_scans = 0, c_tests = 0;
+  SearchStats stats;
   unsigned long long c_iters = 0, c_corr = 0;
+  const unsigned long long n_items =
+      P.resume ? (unsigned long long)(*P.in_count) : (unsigned long long)P.n_pairs;
 
   for (;;) {
-    /* ---- fetch the next pair ---------------------------------------------------------------- */
+    /* ---- fetch the next work item ----------------------------------------------------------- */
     if (tid == 0) {
       const unsigned long long k = atomicAdd(P.queue, 1ull);
       L.ctl[0] = (int32_t)(k & 0xffffffffu);
       L.ctl[1] = (int32_t)(k >> 32);
     }
     __syncthreads();
-    const long long pair = (long long)(((unsigned long long)(uint32_t)L.ctl[1] << 32) | (uint32_t)L.ctl[0]);
-    if (pair >= P.n_pairs) break;
+    const unsigned long long item = ((unsigned long long)(uint32_t)L.ctl[1] << 32) | (uint32_t)L.ctl[0];
+    if (item >= n_items) break;
+    const long long pair = P.resume ? P.susp_in[item] : (long long)item;
+    const unsigned char *slot_in = P.resume ? P.state_in + (size_t)item * (size_t)P.slot_bytes : nullptr;
     const PairTask task = P.tasks[pair];
     const float2 *srow = P.store.pts + (size_t)task.src * P.store.pitch;
     const float2 *trow = P.store.pts + (size_t)task.tgt * P.store.pitch;
     const int ns_full = P.store.count[task.src], nt_full = P.store.count[task.tgt];
     const int ns = (ns_full + div - 1) / div, nt = (nt_full + div - 1) / div;
-    const int gs = (ns + kGroup - 1) / kGroup, gt = (nt + kGroup - 1) / kGroup;
+    const int ts = (ns + kTile - 1) / kTile, tt = (nt + kTile - 1) / kTile;   /* tiles           */
+    const int gs = ts * GPT, gt = tt * GPT;                                    /* box groups      */
 
     /* ---- stage both clouds in shared memory ------------------------------------------------- */
-    if (div == 1) {
-      /* contiguous rows: two 1-D TMA bulk copies completing on one mbarrier */
+    {
+      /* contiguous rows: 1-D TMA bulk copies completing on one mbarrier; a resumed pair takes its
+       * current source cloud and neighbour seeds from its state slot */
+      const bool tma_t = (div == 1), tma_s = (div == 1) || P.resume;
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
-        const uint32_t bt = (uint32_t)((nt * 8 + 15) & ~15), bs = (uint32_t)((ns * 8 + 15) & ~15);
-        mbar_expect_tx(L.mbar, bt + bs);
+        const uint32_t bt = tma_t ? (uint32_t)((nt * 8 + 15) & ~15) : 0u;
+        const uint32_t bs = tma_s ? (uint32_t)((ns * 8 + 15) & ~15) : 0u;
+        const uint32_t bn = P.resume ? (uint32_t)((ns * 4 + 15) & ~15) : 0u;
+        mbar_expect_tx(L.mbar, bt + bs + bn);
         if (bt) bulk_g2s(L.tgt, trow, bt, L.mbar);
-        if (bs) bulk_g2s(L.src, srow, bs, L.mbar);
+        if (bs) bulk_g2s(L.src, P.resume ? (const void *)(slot_in + kStateHeader) : (const void *)srow, bs, L.mbar);
+        if (bn) bulk_g2s(L.nn, slot_in + kStateHeader + (size_t)P.n_cap * 8, bn, L.mbar);
       }
+      if (!tma_t) for (int k = tid; k < nt; k += WARPS * 32) L.tgt[k] = __ldg(trow + (size_t)k * div);
+      if (!tma_s) for (int k = tid; k < ns; k += WARPS * 32) L.src[k] = __ldg(srow + (size_t)k * div);
       mbar_wait(L.mbar, mbar_phase);
       mbar_phase ^= 1u;
-    } else {
-      for (int k = tid; k < nt; k += WARPS * 32) L.tgt[k] = __ldg(trow + (size_t)k * div);
-      for (int k = tid; k < ns; k += WARPS * 32) L.src[k] = __ldg(srow + (size_t)k * div);
     }
     __syncthreads();
-    /* pad to whole groups, apply the guess (PCL transformCloud(input, guess), App. A.2), boxes */
-    for (int k = nt + tid; k < gt * kGroup; k += WARPS * 32) L.tgt[k] = make_float2(kPad, kPad);
-    for (int k = ns + tid; k < gs * kGroup; k += WARPS * 32) L.src[k] = make_float2(kPad, kPad);
+    /* pad to whole tiles, apply the guess (PCL transformCloud(input, guess), App. A.2), boxes */
+    for (int k = nt + tid; k < tt * kTile; k += WARPS * 32) L.tgt[k] = make_float2(kPad, kPad);
+    for (int k = ns + tid; k < ts * kTile; k += WARPS * 32) L.src[k] = make_float2(kPad, kPad);
     __syncthreads();
-    for (int g = warp; g < gt; g += WARPS) {
-      const int k = g * kGroup + lane;
-      const float4 b = warp_box(L.tgt[k], k < nt);
-      if (lane == 0) L.tbox[g] = b;
+    for (int t = warp; t < tt; t += WARPS) {
+      const int k = t * kTile + lane;
+      store_tile_boxes(L.tgt[k], k < nt, t, L.tbox, nullptr);
     }
-    for (int g = warp; g < gs; g += WARPS) {
-      const int k = g * kGroup + lane;
+    for (int t = warp; t < ts; t += WARPS) {
+      const int k = t * kTile + lane;
       float2 p = L.src[k];
-      if (k < ns) { p = xform(task.c, task.s, task.tx, task.ty, p); L.src[k] = p; }
-      L.nn[k] = -1;
-      const float4 b = warp_box(p, k < ns);
-      if (lane == 0) L.sbox[g] = b;
+      if (!P.resume) {
+        if (k < ns) { p = xform(task.c, task.s, task.tx, task.ty, p); L.src[k] = p; }
+        L.nn[k] = -1;
+      }
+      store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
     }
     if (tid < 16) L.red[tid] = 0;
     __syncthreads();
 
     /* ---- parity hook: a single correspondence pass ------------------------------------------ */
     if (P.corr_out != nullptr) {
-      for (int tile = warp; tile < gs; tile += WARPS) {
+      for (int tile = warp; tile < ts; tile += WARPS) {
         float2 q; int j; float d; bool fwd;
         const bool acc = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
-                                            c_scans, c_tests);
-        const int i = tile * kGroup + lane;
+                                            stats);
+        const int i = tile * kTile + lane;
         if (i < ns) {
           P.corr_out[i] = acc ? j : -1;
           P.corr_d2_out[i] = fwd ? d : __int_as_float(0x7f800000);
@@ -516,15 +584,21 @@ __global__ void __launch_bounds__(WARPS * 32) icp_pairs_kernel(const KernelParam
     uint32_t status = 0;
     double mse = 0.0, mse_prev = 1.7976931348623157e308;
     if (ns <= 0 || nt <= 0) status |= DPGICP_FLAG_EMPTY_INPUT;
+    if (P.resume && tid == 0) {
+      const SuspHeader h = *reinterpret_cast<const SuspHeader *>(slot_in);
+      fc = h.fc; fs = h.fs; ftx = h.ftx; fty = h.fty;
+      mse = h.mse; mse_prev = h.mse_prev; iterations = h.iterations; last_k = h.last_k; status = h.status;
+    }
 
+    int stop = 0;
     for (;;) {
       long long m_px = 0, m_py = 0, m_qx = 0, m_qy = 0, m_xx = 0, m_xy = 0, m_yx = 0, m_yy = 0, m_d2 = 0;
       int m_k = 0;
-      for (int tile = warp; tile < gs; tile += WARPS) {
+      for (int tile = warp; tile < ts; tile += WARPS) {
         float2 q; int j; float d; bool fwd;
         const bool acc = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
-                                            c_scans, c_tests);
-        const int i = tile * kGroup + lane;
+                                            stats);
+        const int i = tile * kTile + lane;
         if (i < ns) L.nn[i] = fwd ? j : -1;           /* seed of the next pass */
         if (acc) {
           const float2 t = L.tgt[j];
@@ -557,13 +631,16 @@ __global__ void __launch_bounds__(WARPS * 32) icp_pairs_kernel(const KernelParam
       __syncthreads();
 
       if (tid == 0) {
+        /* has this stage's queue run dry?  (read early, the L2 round trip overlaps the solve) */
+        unsigned long long qhead = 0;
+        if (P.out_count != nullptr) qhead = *reinterpret_cast<volatile unsigned long long *>(P.queue);
         /* rigid step: planar Procrustes in binary64 (PCL TransformationEstimationSVD, z = 0) */
         const int K = (int)L.red[9];
         last_k = K;
-        int stop = 0;
+        int st = 0;
         if (K < 3) {                                   /* App. A.3-4 */
           status |= DPGICP_STOP_NO_CORRESPONDENCES;
-          stop = 2;
+          st = 2;
         } else {
           const double Kd = (double)K;
           const double spx = __dmul_rn((double)L.red[0], 1.0 / kScaleLin);
@@ -596,33 +673,37 @@ __global__ void __launch_bounds__(WARPS * 32) icp_pairs_kernel(const KernelParam
           const double cos_angle = __dmul_rn(0.5, (double)tr);
           const float tsq = __fadd_rn(__fmul_rn(stx, stx), __fmul_rn(sty, sty));
           if (iterations >= P.max_iterations) {
-            status |= DPGICP_STOP_ITERATIONS | DPGICP_FLAG_CONVERGED; stop = 1;
+            status |= DPGICP_STOP_ITERATIONS | DPGICP_FLAG_CONVERGED; st = 1;
           } else if (cos_angle >= P.rot_thr && (double)tsq <= P.eps) {
-            status |= DPGICP_STOP_TRANSFORM | DPGICP_FLAG_CONVERGED; stop = 1;
+            status |= DPGICP_STOP_TRANSFORM | DPGICP_FLAG_CONVERGED; st = 1;
           } else if (fabs(__dsub_rn(mse, mse_prev)) < 1e-12) {
-            status |= DPGICP_STOP_ABS_MSE | DPGICP_FLAG_CONVERGED; stop = 1;
+            status |= DPGICP_STOP_ABS_MSE | DPGICP_FLAG_CONVERGED; st = 1;
           } else {
             mse_prev = mse;
+            if (P.out_count != nullptr && qhead >= n_items) {
+              /* queue dry: hand this pair to the next (wider) stage */
+              st = 3;
+              L.ctl[4] = (int32_t)atomicAdd(P.out_count, 1u);
+            }
           }
         }
-        L.ctl[2] = stop;
+        L.ctl[2] = st;
         L.ctl[3] = K;
 #pragma unroll
         for (int k = 0; k < 10; ++k) L.red[k] = 0;
       }
       __syncthreads();
-      const int stop = L.ctl[2];
+      stop = L.ctl[2];
       c_corr += (tid == 0) ? (unsigned long long)L.ctl[3] : 0ull;
       if (stop == 2) break;
       /* src' = step * src' in place (App. A.3-6) and refresh the source boxes */
       {
         const float sc = L.step[0], ss = L.step[1], stx = L.step[2], sty = L.step[3];
-        for (int g = warp; g < gs; g += WARPS) {
-          const int k = g * kGroup + lane;
+        for (int t = warp; t < ts; t += WARPS) {
+          const int k = t * kTile + lane;
           float2 p = L.src[k];
           if (k < ns) { p = xform(sc, ss, stx, sty, p); L.src[k] = p; }
-          const float4 b = warp_box(p, k < ns);
-          if (lane == 0) L.sbox[g] = b;
+          store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
         }
       }
       if (tid == 0) ++c_iters;
@@ -630,8 +711,29 @@ __global__ void __launch_bounds__(WARPS * 32) icp_pairs_kernel(const KernelParam
       if (stop) break;
     }
 
-    /* ---- covariance (calculate_ICP_COV) + result record -------------------------------------- */
+    if (stop == 3) {
+      /* ---- suspend: current source cloud + seeds + scalars -> state slot, pair -> next queue --- */
+      unsigned char *slot = P.state_out + (size_t)(uint32_t)L.ctl[4] * (size_t)P.slot_bytes;
+      float2 *s_src = reinterpret_cast<float2 *>(slot + kStateHeader);
+      int32_t *s_nn = reinterpret_cast<int32_t *>(slot + kStateHeader + (size_t)P.n_cap * 8);
+      for (int k = tid; k < ns; k += WARPS * 32) { s_src[k] = L.src[k]; s_nn[k] = L.nn[k]; }
+      if (tid == 0) {
+        SuspHeader h;
+        h.fc = fc; h.fs = fs; h.ftx = ftx; h.fty = fty; h.mse = mse; h.mse_prev = mse_prev;
+        h.iterations = iterations; h.last_k = last_k; h.status = status; h.pad = 0;
+        *reinterpret_cast<SuspHeader *>(slot) = h;
+        P.susp_out[(uint32_t)L.ctl[4]] = pair;
+      }
+      continue;            /* the queue is dry: the next fetch ends this CTA */
+    }
+
+    /* ---- covariance (calculate_ICP_COV) + result record --------------------------------------
+     * The 11 binary64 sums are formed in an order that does not depend on WARPS (a pair may finish in
+     * any stage): per 32-element tile by a fixed xor-shuffle tree, tiles added in ascending order by
+     * thread 0, 16 tile partials at a time through L.dpart. */
     double S[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) S[k] = 0.0;
     uint32_t cov_flag = 0;
     const int cov_mode = P.cov_mode;
     if (cov_mode != DPGICP_COV_REFERENCE_LIVE) {
@@ -642,56 +744,72 @@ __global__ void __launch_bounds__(WARPS * 32) icp_pairs_kernel(const KernelParam
       const double x = (double)Ttx, y = (double)Tty;
       const double a = (double)atan2f(Ts, Tc);
       const double ca = cos(a), sa = sin(a);
-      double acc[11];
-#pragma unroll
-      for (int k = 0; k < 11; ++k) acc[k] = 0.0;
+      int n_cov = 0, nd = 0;
       if (cov_mode == DPGICP_COV_CENSI_INDEXPAIR) {
         /* full clouds paired by index (dpg_slam.cc:430), Hessian over all, D-term over the cap */
-        const int nh = ns_full < nt_full ? ns_full : nt_full;
-        const int nd = (P.cov_cap > 0 && nh > P.cov_cap) ? P.cov_cap : nh;
-        for (int k = tid; k < nh; k += WARPS * 32) {
-          const float2 p = __ldg(srow + k), q = __ldg(trow + k);
-          cov_terms(p.x, p.y, q.x, q.y, ca, sa, x, y, true, k < nd, acc);
-        }
+        n_cov = ns_full < nt_full ? ns_full : nt_full;
+        nd = (P.cov_cap > 0 && n_cov > P.cov_cap) ? P.cov_cap : n_cov;
       } else {
         /* CENSI_CORR: correspondences at the final pose: src'' = final * src (original points) */
         __syncthreads();
-        for (int g = warp; g < gs; g += WARPS) {
-          const int k = g * kGroup + lane;
+        for (int t = warp; t < ts; t += WARPS) {
+          const int k = t * kTile + lane;
           float2 p = make_float2(kPad, kPad);
           if (k < ns) { p = xform(Tc, Ts, Ttx, Tty, __ldg(srow + (size_t)k * div)); }
           L.src[k] = p;
-          const float4 b = warp_box(p, k < ns);
-          if (lane == 0) L.sbox[g] = b;
+          store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
         }
         __syncthreads();
-        for (int tile = warp; tile < gs; tile += WARPS) {
+        for (int tile = warp; tile < ts; tile += WARPS) {
           float2 q; int j; float d; bool fwd;
           const bool ok = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
-                                             c_scans, c_tests);
+                                             stats);
           const unsigned bal = __ballot_sync(0xffffffffu, ok);
-          const int i = tile * kGroup + lane;
+          const int i = tile * kTile + lane;
           if (i < ns) L.nn[i] = ok ? j : -1;
           if (lane == 0) L.tcnt[tile] = __popc(bal);
         }
         __syncthreads();
-        for (int tile = warp; tile < gs; tile += WARPS) {
-          int prefix = 0;
-          for (int t = lane; t < tile; t += 32) prefix += L.tcnt[t];
-          prefix = __reduce_add_sync(0xffffffffu, prefix);
-          const int i = tile * kGroup + lane;
-          const int j = (i < ns) ? L.nn[i] : -1;
-          const unsigned bal = __ballot_sync(0xffffffffu, j >= 0);
-          const int rank = prefix + __popc(bal & ((1u << lane) - 1u));
-          if (j >= 0) {
-            const float2 p = __ldg(srow + (size_t)i * div);
-            const float2 q = L.tgt[j];
-            const bool in_d = (P.cov_cap <= 0) || (rank < P.cov_cap);
-            cov_terms(p.x, p.y, q.x, q.y, ca, sa, x, y, true, in_d, acc);
-          }
-        }
+        n_cov = ns;
       }
-      block_sum11<WARPS>(acc, L.dpart, S);
+      const int cov_tiles = (n_cov + kTile - 1) / kTile;
+      for (int chunk = 0; chunk < cov_tiles; chunk += kMaxWarps) {
+        const int chunk_end = chunk + kMaxWarps < cov_tiles ? chunk + kMaxWarps : cov_tiles;
+        for (int tile = chunk + warp; tile < chunk_end; tile += WARPS) {
+          double acc[11];
+#pragma unroll
+          for (int k = 0; k < 11; ++k) acc[k] = 0.0;
+          const int i = tile * kTile + lane;
+          if (cov_mode == DPGICP_COV_CENSI_INDEXPAIR) {
+            if (i < n_cov) {
+              const float2 p = __ldg(srow + i), q = __ldg(trow + i);
+              cov_terms(p.x, p.y, q.x, q.y, ca, sa, x, y, true, i < nd, acc);
+            }
+          } else {
+            int prefix = 0;
+            for (int t = lane; t < tile; t += 32) prefix += L.tcnt[t];
+            prefix = __reduce_add_sync(0xffffffffu, prefix);
+            const int j = (i < ns) ? L.nn[i] : -1;
+            const unsigned bal = __ballot_sync(0xffffffffu, j >= 0);
+            const int rank = prefix + __popc(bal & ((1u << lane) - 1u));
+            if (j >= 0) {
+              const float2 p = __ldg(srow + (size_t)i * div);
+              const float2 q = L.tgt[j];
+              const bool in_d = (P.cov_cap <= 0) || (rank < P.cov_cap);
+              cov_terms(p.x, p.y, q.x, q.y, ca, sa, x, y, true, in_d, acc);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 11; ++k) acc[k] = warp_sum_f64(acc[k]);
+          if (lane == 0)
+            for (int k = 0; k < 11; ++k) L.dpart[(tile - chunk) * 12 + k] = acc[k];
+        }
+        __syncthreads();
+        if (tid == 0)
+          for (int t = 0; t < chunk_end - chunk; ++t)
+            for (int k = 0; k < 11; ++k) S[k] = __dadd_rn(S[k], L.dpart[t * 12 + k]);
+        __syncthreads();
+      }
     }
 
     if (tid == 0) {
@@ -716,8 +834,13 @@ __global__ void __launch_bounds__(WARPS * 32) icp_pairs_kernel(const KernelParam
 
   /* executed-work counters (one set of atomics per CTA) */
   if (lane == 0) {
-    atomicAdd(P.counters + 2, (unsigned long long)c_scans * (kGroup * 32ull));
-    atomicAdd(P.counters + 3, (unsigned long long)c_tests * 32ull);
+    atomicAdd(P.counters + 2, (unsigned long long)stats.scans * (kGroup * 32ull));
+    atomicAdd(P.counters + 3, (unsigned long long)stats.tests * 32ull);
+#ifdef DPGICP_STATS
+    atomicAdd(P.counters + 5, (unsigned long long)stats.cands);
+    atomicAdd(P.counters + 6, (unsigned long long)stats.loose);
+    atomicAdd(P.counters + 7, (unsigned long long)stats.searches);
+#endif
   }
   if (tid == 0) {
     atomicAdd(P.counters + 0, c_iters);

@@ -169,7 +169,8 @@ class ScanMatcher:
         c = (C.c_uint64 * 8)()
         self._check(self._lib.dpgicp_last_run_counters(self._h, C.byref(c)))
         return {"iterations": int(c[0]), "correspondences": int(c[1]), "distance_evals": int(c[2]),
-                "box_tests": int(c[3]), "kernel_launches": int(c[4])}
+                "box_tests": int(c[3]), "kernel_launches": int(c[4]),
+                "dev_candidates": int(c[5]), "dev_loose_searches": int(c[6]), "dev_searches": int(c[7])}
 
     def fp32_probe(self) -> dict:
         """Measured FP32 CUDA-core rates of this GPU (ops/s): separately rounded FMUL+FADD and FFMA."""

@@ -33,38 +33,36 @@ def main():
     n_pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
     torch.cuda.init()
     print(torch.cuda.get_device_name(0), flush=True)
-    t = time.time()
     if which == "corridor":
         wl = synth.config_corridor(n_pairs=n_pairs, seed=2)
     else:
         wl = synth.config_loop_closure(n_pairs=n_pairs, n_scans=2000, seed=3)
-    print("synth s", time.time() - t, flush=True)
     out = {}
-    for warps in (0, 1, 2, 4, 8):
-        for ctas in (0, 1, 2, 4, 8):
-            if warps == 0 and ctas != 0 or warps != 0 and ctas == 0:
-                continue
-            os.environ["DPGICP_WARPS"] = str(warps)
-            os.environ["DPGICP_CTAS_PER_SM"] = str(ctas)
-            with ScanMatcher(0) as sm:
-                sm.upload_ranges(wl.ranges, wl.scanner)
-                sm.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
-                for search in (1, 0):
-                    for div in (1, 5):
-                        p = Params.defaults(downsample_divisor=div, cov_mode=COV_CENSI_CORR, search=search)
-                        try:
-                            best, med = time_run(sm, p)
-                        except Exception as e:
-                            print("ERR", warps, ctas, search, div, e, flush=True)
-                            continue
-                        c = sm.last_run_counters()
-                        r = sm.fetch_results()
-                        key = f"w{warps}_c{ctas}_s{search}_d{div}"
-                        out[key] = dict(ms=best, med=med, pairs_per_s=wl.n_pairs / best * 1e3,
-                                        iters=c["iterations"], evals=c["distance_evals"], tests=c["box_tests"],
-                                        mean_it=float(r["iterations"].mean()), max_it=int(r["iterations"].max()))
-                        print(key, json.dumps(out[key]), flush=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"probe_{which}.json"), "w") as f:
+    combos = [(st, w, c) for st in (1, 2, 3) for w in (0, 2, 4, 8) for c in (0,)] + [(3, 4, 4), (3, 4, 3), (1, 4, 6)]
+    for stages, warps, ctas in combos:
+        os.environ["DPGICP_STAGES"] = str(stages)
+        os.environ["DPGICP_WARPS"] = str(warps)
+        os.environ["DPGICP_CTAS_PER_SM"] = str(ctas)
+        with ScanMatcher(0) as sm:
+            sm.upload_ranges(wl.ranges, wl.scanner)
+            sm.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
+            for search in (1, 0):
+                for div in (1, 5):
+                    if search == 0 and (stages != 3 or warps != 0):
+                        continue
+                    p = Params.defaults(downsample_divisor=div, cov_mode=COV_CENSI_CORR, search=search)
+                    try:
+                        best, med = time_run(sm, p)
+                    except Exception as e:
+                        print("ERR", stages, warps, ctas, search, div, e, flush=True)
+                        continue
+                    c = sm.last_run_counters()
+                    key = f"st{stages}_w{warps}_c{ctas}_s{search}_d{div}"
+                    out[key] = dict(ms=best, med=med, pairs_per_s=wl.n_pairs / best * 1e3, evals=c["distance_evals"],
+                                    tests=c["box_tests"])
+                    print(key, json.dumps(out[key]), flush=True)
+    tag = os.path.basename(os.environ.get("DPGICP_LIBRARY", "default")).replace(".so", "")
+    with open(os.path.join(ROOT, "gpurun_out", f"probe_{which}_{n_pairs}_{tag}.json"), "w") as f:
         json.dump(out, f, indent=1)
 
 
