@@ -37,28 +37,53 @@ if ROOT not in sys.path:
 
 METRIC = "icp_cov_scan_pairs_per_sec"
 UNIT = "pairs/s"
-PAIRS_PER_GPU = 5000
-N_BEAMS = 1081
+# The headline workload is BASELINE configs[1]; the others are the remaining single-GPU-sized configs, selectable
+# with --workload for additional measurements (they are parity-test cases first, not the bench line).
+WORKLOADS = {
+    "corridor": dict(desc="BASELINE configs[1]: synthetic corridor trajectory, 5000 sequential odometry scan pairs per GPU",
+                     pairs_per_gpu=5000, beams=1081, seed=2, metric=0),
+    "loop_closure": dict(desc="BASELINE configs[2]: loop-closure candidate sweep, 100k scan pairs over 2000 scans with random "
+                              "initial offsets, per GPU", pairs_per_gpu=100_000, beams=1081, seed=3, metric=0),
+    "dense": dict(desc="BASELINE configs[3] shape: dense 4096-beam scans, point-to-line, 125k pairs per GPU (1M over 8 GPUs)",
+                  pairs_per_gpu=125_000, beams=4096, seed=4, metric=1),
+}
+WORKLOAD = "corridor"
+PAIRS_PER_GPU = WORKLOADS[WORKLOAD]["pairs_per_gpu"]
+N_BEAMS = WORKLOADS[WORKLOAD]["beams"]
+
+
+def select_workload(name: str):
+    global WORKLOAD, PAIRS_PER_GPU, N_BEAMS
+    WORKLOAD = name
+    PAIRS_PER_GPU = WORKLOADS[name]["pairs_per_gpu"]
+    N_BEAMS = WORKLOADS[name]["beams"]
 
 
 # ---- workload ----------------------------------------------------------------------------------------------
-def make_workload(n_pairs: int, seed: int = 2):
+def make_workload(n_pairs: int):
     from dpg_slam_b200 import synth
-    return synth.config_corridor(n_pairs=n_pairs, n_beams=N_BEAMS, seed=seed)
+    w = WORKLOADS[WORKLOAD]
+    if WORKLOAD == "corridor":
+        return synth.config_corridor(n_pairs=n_pairs, n_beams=N_BEAMS, seed=w["seed"])
+    if WORKLOAD == "loop_closure":
+        return synth.config_loop_closure(n_pairs=n_pairs, n_scans=2000, n_beams=N_BEAMS, seed=w["seed"])
+    return synth.config_loop_closure(n_pairs=n_pairs, n_scans=20_000, n_beams=N_BEAMS, seed=w["seed"])
 
 
 def bench_params():
     from dpg_slam_b200._abi import COV_CENSI_CORR, Params
-    return Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR)
+    return Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR, metric=WORKLOADS[WORKLOAD]["metric"])
 
 
 def workload_config(n_gpus: int, extra=None):
-    cfg = {"workload": "BASELINE configs[1]: synthetic corridor trajectory, 5000 sequential odometry scan pairs per GPU",
+    w = WORKLOADS[WORKLOAD]
+    cfg = {"workload": w["desc"],
            "pairs_per_gpu": PAIRS_PER_GPU, "global_pairs": PAIRS_PER_GPU * n_gpus, "beams": N_BEAMS,
-           "fov_deg": 270, "downsample_divisor": 1, "metric_kind": "point_to_point", "reciprocal": True,
+           "fov_deg": 270, "downsample_divisor": 1, "metric_kind": "point_to_line" if w["metric"] else "point_to_point",
+           "reciprocal": True,
            "cov_mode": "CENSI_CORR(cap 200)", "max_iterations": 500, "max_correspondence_distance_m": 0.6,
            "search": "exact pruned (bounding-box groups)", "sharding": f"round-robin over {n_gpus} GPU(s), scan store replicated",
-           "l2": "flushed between timed steps (512 MiB memset outside the event pair)", "seed": 2}
+           "l2": "flushed between timed steps (512 MiB memset outside the event pair)", "seed": w["seed"]}
     if extra:
         cfg.update(extra)
     return cfg
@@ -369,7 +394,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="corridor", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         return run_reference(args)
     return run_product(args)

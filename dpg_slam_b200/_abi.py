@@ -19,7 +19,7 @@ METRIC_POINT_TO_POINT, METRIC_POINT_TO_LINE = 0, 1
 SEARCH_BRUTE, SEARCH_PRUNED = 0, 1
 COV_REFERENCE_LIVE, COV_CENSI_INDEXPAIR, COV_CENSI_CORR = 0, 1, 2
 STOP_MASK = 0xFF
-STOP_NONE, STOP_ITERATIONS, STOP_TRANSFORM, STOP_ABS_MSE, STOP_NO_CORRESPONDENCES = 0, 1, 2, 3, 4
+STOP_NONE, STOP_ITERATIONS, STOP_TRANSFORM, STOP_ABS_MSE, STOP_NO_CORRESPONDENCES, STOP_DEGENERATE = 0, 1, 2, 3, 4, 5
 FLAG_CONVERGED, FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT = 0x100, 0x200, 0x400
 MAX_ABS_COORD = 1000.0
 MAX_POINTS = 8192

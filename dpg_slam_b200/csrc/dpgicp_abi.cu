@@ -100,8 +100,8 @@ int check_params(dpgicp_ctx *ctx, const dpgicp_params *p) {
   if (!(p->max_correspondence_distance > 0.0) || !std::isfinite(p->max_correspondence_distance))
     return fail(ctx, DPGICP_E_INVALID, "max_correspondence_distance must be positive and finite");
   if (!(p->transformation_epsilon >= 0.0)) return fail(ctx, DPGICP_E_INVALID, "transformation_epsilon must be >= 0");
-  if (p->metric != DPGICP_METRIC_POINT_TO_POINT)
-    return fail(ctx, DPGICP_E_INVALID, "metric: only DPGICP_METRIC_POINT_TO_POINT is implemented");
+  if (p->metric != DPGICP_METRIC_POINT_TO_POINT && p->metric != DPGICP_METRIC_POINT_TO_LINE)
+    return fail(ctx, DPGICP_E_INVALID, "metric must be DPGICP_METRIC_POINT_TO_POINT or DPGICP_METRIC_POINT_TO_LINE");
   if (p->search != DPGICP_SEARCH_BRUTE && p->search != DPGICP_SEARCH_PRUNED)
     return fail(ctx, DPGICP_E_INVALID, "search must be DPGICP_SEARCH_BRUTE or DPGICP_SEARCH_PRUNED");
   if (p->cov_mode < DPGICP_COV_REFERENCE_LIVE || p->cov_mode > DPGICP_COV_CENSI_CORR)

@@ -464,6 +464,69 @@ __device__ __forceinline__ void block_sum11(double *acc, double *dpart, double *
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Rigid steps (thread 0 of the CTA), mirroring oracle/dpg_oracle.c operation for operation.
+ * red[0..8] = nine exact fixed-point sums (meaning depends on the metric), red[9] = sum d2, red[10] = K
+ * ---------------------------------------------------------------------------------------------- */
+/* point-to-point: planar Procrustes in binary64 (PCL TransformationEstimationSVD on z = 0 data) */
+__device__ __forceinline__ void solve_p2p(const long long *red, double Kd, float st[4]) {
+  const double spx = __dmul_rn((double)red[0], 1.0 / kScaleLin);
+  const double spy = __dmul_rn((double)red[1], 1.0 / kScaleLin);
+  const double sqx = __dmul_rn((double)red[2], 1.0 / kScaleLin);
+  const double sqy = __dmul_rn((double)red[3], 1.0 / kScaleLin);
+  const double dot = __dmul_rn((double)(red[4] + red[7]), 1.0 / kScaleProd);
+  const double crs = __dmul_rn((double)(red[5] - red[6]), 1.0 / kScaleProd);
+  const double a = __dsub_rn(dot, __ddiv_rn(__dadd_rn(__dmul_rn(spx, sqx), __dmul_rn(spy, sqy)), Kd));
+  const double b = __dsub_rn(crs, __ddiv_rn(__dsub_rn(__dmul_rn(spx, sqy), __dmul_rn(spy, sqx)), Kd));
+  const double h = __dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+  double c = 1.0, s = 0.0;
+  if (h > 0.0) { c = __ddiv_rn(a, h); s = __ddiv_rn(b, h); }
+  const double mpx = __ddiv_rn(spx, Kd), mpy = __ddiv_rn(spy, Kd);
+  const double mqx = __ddiv_rn(sqx, Kd), mqy = __ddiv_rn(sqy, Kd);
+  const double tx = __dsub_rn(mqx, __dsub_rn(__dmul_rn(c, mpx), __dmul_rn(s, mpy)));
+  const double ty = __dsub_rn(mqy, __dadd_rn(__dmul_rn(s, mpx), __dmul_rn(c, mpy)));
+  st[0] = (float)c; st[1] = (float)s; st[2] = (float)tx; st[3] = (float)ty;
+}
+
+/* point-to-line: one Gauss-Newton step from the 3x3 normal equations, Cholesky; the rotation is the
+ * Cayley map of dtheta/2 (rational, no libm).  Returns false when A is not positive definite. */
+__device__ __forceinline__ bool solve_p2l(const long long *red, float st[4]) {
+  const double inv = 1.0 / kScaleProd;
+  const double a11 = __dmul_rn((double)red[0], inv), a12 = __dmul_rn((double)red[1], inv);
+  const double a13 = __dmul_rn((double)red[2], inv), a22 = __dmul_rn((double)red[3], inv);
+  const double a23 = __dmul_rn((double)red[4], inv), a33 = __dmul_rn((double)red[5], inv);
+  const double b1 = -__dmul_rn((double)red[6], inv), b2 = -__dmul_rn((double)red[7], inv);
+  const double b3 = -__dmul_rn((double)red[8], inv);
+  if (!(a11 > 0.0)) return false;
+  const double l11 = __dsqrt_rn(a11);
+  const double l21 = __ddiv_rn(a12, l11), l31 = __ddiv_rn(a13, l11);
+  const double d22 = __dsub_rn(a22, __dmul_rn(l21, l21));
+  if (!(d22 > 0.0)) return false;
+  const double l22 = __dsqrt_rn(d22);
+  const double l32 = __ddiv_rn(__dsub_rn(a23, __dmul_rn(l31, l21)), l22);
+  const double d33 = __dsub_rn(__dsub_rn(a33, __dmul_rn(l31, l31)), __dmul_rn(l32, l32));
+  if (!(d33 > 0.0)) return false;
+  const double l33 = __dsqrt_rn(d33);
+  const double y1 = __ddiv_rn(b1, l11);
+  const double y2 = __ddiv_rn(__dsub_rn(b2, __dmul_rn(l21, y1)), l22);
+  const double y3 = __ddiv_rn(__dsub_rn(__dsub_rn(b3, __dmul_rn(l31, y1)), __dmul_rn(l32, y2)), l33);
+  const double x3 = __ddiv_rn(y3, l33);
+  const double x2 = __ddiv_rn(__dsub_rn(y2, __dmul_rn(l32, x3)), l22);
+  const double x1 = __ddiv_rn(__dsub_rn(__dsub_rn(y1, __dmul_rn(l21, x2)), __dmul_rn(l31, x3)), l11);
+  if (!isfinite(x1) || !isfinite(x2) || !isfinite(x3)) return false;
+  const double u = __dmul_rn(0.5, x3);
+  const double uu = __dmul_rn(u, u);
+  const double den = __dadd_rn(1.0, uu);
+  st[0] = (float)__ddiv_rn(__dsub_rn(1.0, uu), den);
+  st[1] = (float)__ddiv_rn(__dadd_rn(u, u), den);
+  st[2] = (float)x1;
+  st[3] = (float)x2;
+  return true;
+}
+
+/* fixed-point term: round-to-nearest-even of v * 2^28 */
+__device__ __forceinline__ long long fxp(double v) { return __double2ll_rn(__dmul_rn(v, kScaleProd)); }
+
+/* ------------------------------------------------------------------------------------------------
  * The persistent ICP + covariance kernel.
  *
  * Staged execution.  ICP iteration counts are heavy-tailed (corridor workload: median 37, p99 174,
@@ -592,7 +655,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
 
     int stop = 0;
     for (;;) {
-      long long m_px = 0, m_py = 0, m_qx = 0, m_qy = 0, m_xx = 0, m_xy = 0, m_yx = 0, m_yy = 0, m_d2 = 0;
+      long long m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, m6 = 0, m7 = 0, m8 = 0, m_d2 = 0;
       int m_k = 0;
       for (int tile = warp; tile < ts; tile += WARPS) {
         float2 q; int j; float d; bool fwd;
@@ -603,30 +666,72 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         if (acc) {
           const float2 t = L.tgt[j];
           const double px = q.x, py = q.y, qx = t.x, qy = t.y;
-          m_px += __double2ll_rn(__dmul_rn(px, kScaleLin));
-          m_py += __double2ll_rn(__dmul_rn(py, kScaleLin));
-          m_qx += __double2ll_rn(__dmul_rn(qx, kScaleLin));
-          m_qy += __double2ll_rn(__dmul_rn(qy, kScaleLin));
-          m_xx += __double2ll_rn(__dmul_rn(__dmul_rn(px, qx), kScaleProd));
-          m_xy += __double2ll_rn(__dmul_rn(__dmul_rn(px, qy), kScaleProd));
-          m_yx += __double2ll_rn(__dmul_rn(__dmul_rn(py, qx), kScaleProd));
-          m_yy += __double2ll_rn(__dmul_rn(__dmul_rn(py, qy), kScaleProd));
+          if (P.metric == DPGICP_METRIC_POINT_TO_LINE) {
+            /* line through the matched target point and its closer beam neighbour (oracle:
+             * accumulate_normal_eq); m0..m5 = A (11,12,13,22,23,33), m6..m8 = sum J^T r */
+            int j2 = -1;
+            float best = __int_as_float(0x7f800000);
+            if (j - 1 >= 0) { const float2 a = L.tgt[j - 1]; best = dist2(q.x, q.y, a.x, a.y); j2 = j - 1; }
+            if (j + 1 < nt) {
+              const float2 a = L.tgt[j + 1];
+              const float dn = dist2(q.x, q.y, a.x, a.y);
+              if (dn < best) { best = dn; j2 = j + 1; }
+            }
+            bool line = false;
+            double nx = 0.0, ny = 0.0;
+            if (j2 >= 0) {
+              const float2 a = L.tgt[j2];
+              const float seg = dist2(a.x, a.y, t.x, t.y);
+              if (seg > 0.0f && seg <= P.gate) {
+                const double tx = __dsub_rn((double)a.x, qx), ty = __dsub_rn((double)a.y, qy);
+                const double len = __dsqrt_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)));
+                nx = __ddiv_rn(-ty, len);
+                ny = __ddiv_rn(tx, len);
+                line = true;
+              }
+            }
+            const double ex = __dsub_rn(px, qx), ey = __dsub_rn(py, qy);
+            if (line) {
+              const double r = __dadd_rn(__dmul_rn(nx, ex), __dmul_rn(ny, ey));
+              const double j3 = __dsub_rn(__dmul_rn(ny, px), __dmul_rn(nx, py));
+              m0 += fxp(__dmul_rn(nx, nx)); m1 += fxp(__dmul_rn(nx, ny)); m2 += fxp(__dmul_rn(nx, j3));
+              m3 += fxp(__dmul_rn(ny, ny)); m4 += fxp(__dmul_rn(ny, j3)); m5 += fxp(__dmul_rn(j3, j3));
+              m6 += fxp(__dmul_rn(nx, r)); m7 += fxp(__dmul_rn(ny, r)); m8 += fxp(__dmul_rn(j3, r));
+            } else {
+              m0 += fxp(1.0); m2 += fxp(-py);
+              m3 += fxp(1.0); m4 += fxp(px);
+              m5 += fxp(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
+              m6 += fxp(ex); m7 += fxp(ey);
+              m8 += fxp(__dsub_rn(__dmul_rn(px, ey), __dmul_rn(py, ex)));
+            }
+          } else {
+            /* point-to-point moments: sums of p, q (2^32) and of the four products (2^28) */
+            m0 += __double2ll_rn(__dmul_rn(px, kScaleLin));
+            m1 += __double2ll_rn(__dmul_rn(py, kScaleLin));
+            m2 += __double2ll_rn(__dmul_rn(qx, kScaleLin));
+            m3 += __double2ll_rn(__dmul_rn(qy, kScaleLin));
+            m4 += fxp(__dmul_rn(px, qx));
+            m5 += fxp(__dmul_rn(px, qy));
+            m6 += fxp(__dmul_rn(py, qx));
+            m7 += fxp(__dmul_rn(py, qy));
+          }
           m_d2 += __double2ll_rn(__dmul_rn((double)d, kScaleD2));
           m_k += 1;
         }
       }
       /* exact integer reduction: warp shuffles, then one shared atomic per warp and value */
-      m_px = warp_sum_i64(m_px); m_py = warp_sum_i64(m_py); m_qx = warp_sum_i64(m_qx);
-      m_qy = warp_sum_i64(m_qy); m_xx = warp_sum_i64(m_xx); m_xy = warp_sum_i64(m_xy);
-      m_yx = warp_sum_i64(m_yx); m_yy = warp_sum_i64(m_yy); m_d2 = warp_sum_i64(m_d2);
+      m0 = warp_sum_i64(m0); m1 = warp_sum_i64(m1); m2 = warp_sum_i64(m2);
+      m3 = warp_sum_i64(m3); m4 = warp_sum_i64(m4); m5 = warp_sum_i64(m5);
+      m6 = warp_sum_i64(m6); m7 = warp_sum_i64(m7); m8 = warp_sum_i64(m8); m_d2 = warp_sum_i64(m_d2);
       m_k = __reduce_add_sync(0xffffffffu, m_k);
       if (lane == 0) {
         unsigned long long *r = reinterpret_cast<unsigned long long *>(L.red);
-        atomicAdd(r + 0, (unsigned long long)m_px); atomicAdd(r + 1, (unsigned long long)m_py);
-        atomicAdd(r + 2, (unsigned long long)m_qx); atomicAdd(r + 3, (unsigned long long)m_qy);
-        atomicAdd(r + 4, (unsigned long long)m_xx); atomicAdd(r + 5, (unsigned long long)m_xy);
-        atomicAdd(r + 6, (unsigned long long)m_yx); atomicAdd(r + 7, (unsigned long long)m_yy);
-        atomicAdd(r + 8, (unsigned long long)m_d2); atomicAdd(r + 9, (unsigned long long)(long long)m_k);
+        atomicAdd(r + 0, (unsigned long long)m0); atomicAdd(r + 1, (unsigned long long)m1);
+        atomicAdd(r + 2, (unsigned long long)m2); atomicAdd(r + 3, (unsigned long long)m3);
+        atomicAdd(r + 4, (unsigned long long)m4); atomicAdd(r + 5, (unsigned long long)m5);
+        atomicAdd(r + 6, (unsigned long long)m6); atomicAdd(r + 7, (unsigned long long)m7);
+        atomicAdd(r + 8, (unsigned long long)m8); atomicAdd(r + 9, (unsigned long long)m_d2);
+        atomicAdd(r + 10, (unsigned long long)(long long)m_k);
       }
       __syncthreads();
 
@@ -634,31 +739,20 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         /* has this stage's queue run dry?  (read early, the L2 round trip overlaps the solve) */
         unsigned long long qhead = 0;
         if (P.out_count != nullptr) qhead = *reinterpret_cast<volatile unsigned long long *>(P.queue);
-        /* rigid step: planar Procrustes in binary64 (PCL TransformationEstimationSVD, z = 0) */
-        const int K = (int)L.red[9];
+        const int K = (int)L.red[10];
         last_k = K;
         int st = 0;
+        float stp[4];
         if (K < 3) {                                   /* App. A.3-4 */
           status |= DPGICP_STOP_NO_CORRESPONDENCES;
           st = 2;
+        } else if (P.metric == DPGICP_METRIC_POINT_TO_LINE && !solve_p2l(L.red, stp)) {
+          status |= DPGICP_STOP_DEGENERATE;            /* geometry does not constrain the pose */
+          st = 2;
         } else {
           const double Kd = (double)K;
-          const double spx = __dmul_rn((double)L.red[0], 1.0 / kScaleLin);
-          const double spy = __dmul_rn((double)L.red[1], 1.0 / kScaleLin);
-          const double sqx = __dmul_rn((double)L.red[2], 1.0 / kScaleLin);
-          const double sqy = __dmul_rn((double)L.red[3], 1.0 / kScaleLin);
-          const double dot = __dmul_rn((double)(L.red[4] + L.red[7]), 1.0 / kScaleProd);
-          const double crs = __dmul_rn((double)(L.red[5] - L.red[6]), 1.0 / kScaleProd);
-          const double a = __dsub_rn(dot, __ddiv_rn(__dadd_rn(__dmul_rn(spx, sqx), __dmul_rn(spy, sqy)), Kd));
-          const double b = __dsub_rn(crs, __ddiv_rn(__dsub_rn(__dmul_rn(spx, sqy), __dmul_rn(spy, sqx)), Kd));
-          const double h = __dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
-          double c = 1.0, s = 0.0;
-          if (h > 0.0) { c = __ddiv_rn(a, h); s = __ddiv_rn(b, h); }
-          const double mpx = __ddiv_rn(spx, Kd), mpy = __ddiv_rn(spy, Kd);
-          const double mqx = __ddiv_rn(sqx, Kd), mqy = __ddiv_rn(sqy, Kd);
-          const double tx = __dsub_rn(mqx, __dsub_rn(__dmul_rn(c, mpx), __dmul_rn(s, mpy)));
-          const double ty = __dsub_rn(mqy, __dadd_rn(__dmul_rn(s, mpx), __dmul_rn(c, mpy)));
-          const float sc = (float)c, ss = (float)s, stx = (float)tx, sty = (float)ty;
+          if (P.metric != DPGICP_METRIC_POINT_TO_LINE) solve_p2p(L.red, Kd, stp);
+          const float sc = stp[0], ss = stp[1], stx = stp[2], sty = stp[3];
           L.step[0] = sc; L.step[1] = ss; L.step[2] = stx; L.step[3] = sty;
           /* final = step * final (App. A.3-6) */
           const float nc = __fadd_rn(__fmul_rn(sc, fc), __fmul_rn(-ss, fs));
@@ -667,7 +761,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           const float nty = __fadd_rn(__fadd_rn(__fmul_rn(ss, ftx), __fmul_rn(sc, fty)), sty);
           fc = nc; fs = nsn; ftx = ntx; fty = nty;
           ++iterations;
-          mse = __ddiv_rn(__dmul_rn((double)L.red[8], 1.0 / kScaleD2), Kd);
+          mse = __ddiv_rn(__dmul_rn((double)L.red[9], 1.0 / kScaleD2), Kd);
           /* DefaultConvergenceCriteria (App. A.5), in PCL's order */
           const float tr = __fsub_rn(__fadd_rn(__fadd_rn(sc, sc), 1.0f), 1.0f);
           const double cos_angle = __dmul_rn(0.5, (double)tr);
@@ -690,7 +784,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         L.ctl[2] = st;
         L.ctl[3] = K;
 #pragma unroll
-        for (int k = 0; k < 10; ++k) L.red[k] = 0;
+        for (int k = 0; k < 11; ++k) L.red[k] = 0;
       }
       __syncthreads();
       stop = L.ctl[2];

@@ -47,7 +47,10 @@ extern "C" {
 /* ---- enumerations ------------------------------------------------------------------------ */
 /* error metric minimised by each ICP step */
 #define DPGICP_METRIC_POINT_TO_POINT 0   /* what the reference runs (PCL ICP, dpg_slam.cc:387)   */
-#define DPGICP_METRIC_POINT_TO_LINE  1   /* north-star extension; no reference counterpart       */
+#define DPGICP_METRIC_POINT_TO_LINE  1   /* north-star extension; no reference counterpart: each matched
+                                          * target point contributes the line through it and its closer beam
+                                          * neighbour; one Gauss-Newton step per iteration from the 3x3 normal
+                                          * equations (Cholesky); DESIGN.md "point-to-line"               */
 
 /* nearest-neighbour search strategy; both are exact and give identical correspondences */
 #define DPGICP_SEARCH_BRUTE   0
@@ -64,7 +67,9 @@ extern "C" {
 #define DPGICP_STOP_ITERATIONS        1u   /* max_iterations reached (PCL reports converged)     */
 #define DPGICP_STOP_TRANSFORM         2u   /* step below transformation_epsilon                  */
 #define DPGICP_STOP_ABS_MSE           3u   /* |mse - mse_prev| < 1e-12                           */
-#define DPGICP_STOP_NO_CORRESPONDENCES 4u  /* fewer than 3 pairs: the only converged==false case */
+#define DPGICP_STOP_NO_CORRESPONDENCES 4u  /* fewer than 3 pairs: converged == false                 */
+#define DPGICP_STOP_DEGENERATE        5u   /* point-to-line only: normal equations not positive definite
+                                            * (geometry does not constrain the pose); converged == false */
 #define DPGICP_FLAG_CONVERGED         0x100u  /* == what icp.hasConverged() returns, dpg_slam.cc:445 */
 #define DPGICP_FLAG_COV_SINGULAR      0x200u  /* Hessian not invertible; cov fell back to the LIVE diagonal */
 #define DPGICP_FLAG_EMPTY_INPUT       0x400u  /* a cloud of the pair had no points                */

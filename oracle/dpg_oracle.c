@@ -318,6 +318,103 @@ static void solve_rigid_p2p(const moments_t *m, float step[4]) {
   step[3] = (float)ty;
 }
 
+/* ---- point-to-line metric (north-star extension; no reference counterpart, defined HERE) -------
+ * For an accepted correspondence (p = current source point, q = target point j):
+ *   neighbour  j2 = whichever of j-1, j+1 exists and is closer to p (binary32 d2, tie -> j-1)
+ *   segment    usable if 0 < d2(q, q_j2) <= gate (binary32): the beam neighbours lie on one surface
+ *   line row   n = perp(q_j2 - q) / |q_j2 - q|,  r = n . (p - q),  J = [n_x, n_y, n_y p_x - n_x p_y]
+ *   fallback   (no usable segment) two point rows: r = p - q, J = [[1, 0, -p_y], [0, 1, p_x]]
+ * Normal equations A = sum J^T J (6 sums), b = -sum J^T r (3 sums): every term is computed in binary64
+ * with individually rounded operations and added as exact 2^28 fixed point (order independent).
+ * One Gauss-Newton step per ICP iteration: Cholesky of the 3x3, delta = (dx, dy, dth); the rotation
+ * of the step is the Cayley map of dth/2 (rational: no libm, so CPU and GPU agree bit for bit):
+ *   u = dth / 2,  c = (1 - u^2) / (1 + u^2),  s = 2u / (1 + u^2).                                   */
+typedef struct {
+  int64_t a11, a12, a13, a22, a23, a33, b1, b2, b3;   /* 2^28 */
+  int64_t sd2;                                         /* 2^40 */
+  int32_t k;
+} normal_eq_t;
+
+static void accumulate_normal_eq(const float *src_t, const float *tgt, int ns, int nt, const int32_t *corr,
+                                 const float *d2, float gate, normal_eq_t *m) {
+  memset(m, 0, sizeof(*m));
+  for (int i = 0; i < ns; ++i) {
+    const int j = corr[i];
+    if (j < 0) continue;
+    const float pxf = src_t[2 * i], pyf = src_t[2 * i + 1];
+    const float qxf = tgt[2 * j], qyf = tgt[2 * j + 1];
+    int j2 = -1;
+    float best = INFINITY;
+    if (j - 1 >= 0) { best = dist2(pxf, pyf, tgt[2 * (j - 1)], tgt[2 * (j - 1) + 1]); j2 = j - 1; }
+    if (j + 1 < nt) {
+      const float dn = dist2(pxf, pyf, tgt[2 * (j + 1)], tgt[2 * (j + 1) + 1]);
+      if (dn < best) { best = dn; j2 = j + 1; }
+    }
+    int line = 0;
+    double nx = 0.0, ny = 0.0;
+    if (j2 >= 0) {
+      const float seg = dist2(tgt[2 * j2], tgt[2 * j2 + 1], qxf, qyf);
+      if (seg > 0.0f && seg <= gate) {
+        const double tx = (double)tgt[2 * j2] - (double)qxf, ty = (double)tgt[2 * j2 + 1] - (double)qyf;
+        const double len = sqrt((tx * tx) + (ty * ty));
+        nx = -ty / len;
+        ny = tx / len;
+        line = 1;
+      }
+    }
+    const double px = pxf, py = pyf;
+    const double ex = px - (double)qxf, ey = py - (double)qyf;
+    if (line) {
+      const double r = (nx * ex) + (ny * ey);
+      const double j3 = (ny * px) - (nx * py);
+      m->a11 += fx((nx * nx) * SCALE_PROD); m->a12 += fx((nx * ny) * SCALE_PROD); m->a13 += fx((nx * j3) * SCALE_PROD);
+      m->a22 += fx((ny * ny) * SCALE_PROD); m->a23 += fx((ny * j3) * SCALE_PROD); m->a33 += fx((j3 * j3) * SCALE_PROD);
+      m->b1 += fx((nx * r) * SCALE_PROD); m->b2 += fx((ny * r) * SCALE_PROD); m->b3 += fx((j3 * r) * SCALE_PROD);
+    } else {
+      m->a11 += fx(1.0 * SCALE_PROD); m->a13 += fx((-py) * SCALE_PROD);
+      m->a22 += fx(1.0 * SCALE_PROD); m->a23 += fx(px * SCALE_PROD);
+      m->a33 += fx(((px * px) + (py * py)) * SCALE_PROD);
+      m->b1 += fx(ex * SCALE_PROD); m->b2 += fx(ey * SCALE_PROD);
+      m->b3 += fx(((px * ey) - (py * ex)) * SCALE_PROD);
+    }
+    m->sd2 += fx((double)d2[i] * SCALE_D2);
+    m->k++;
+  }
+}
+
+/* returns 0 when the normal equations are not positive definite */
+static int solve_rigid_p2l(const normal_eq_t *m, float step[4]) {
+  const double inv = 1.0 / SCALE_PROD;
+  const double a11 = (double)m->a11 * inv, a12 = (double)m->a12 * inv, a13 = (double)m->a13 * inv;
+  const double a22 = (double)m->a22 * inv, a23 = (double)m->a23 * inv, a33 = (double)m->a33 * inv;
+  const double b1 = -((double)m->b1 * inv), b2 = -((double)m->b2 * inv), b3 = -((double)m->b3 * inv);
+  if (!(a11 > 0.0)) return 0;
+  const double l11 = sqrt(a11);
+  const double l21 = a12 / l11, l31 = a13 / l11;
+  const double d22 = a22 - (l21 * l21);
+  if (!(d22 > 0.0)) return 0;
+  const double l22 = sqrt(d22);
+  const double l32 = (a23 - (l31 * l21)) / l22;
+  const double d33 = (a33 - (l31 * l31)) - (l32 * l32);
+  if (!(d33 > 0.0)) return 0;
+  const double l33 = sqrt(d33);
+  const double y1 = b1 / l11;
+  const double y2 = (b2 - (l21 * y1)) / l22;
+  const double y3 = ((b3 - (l31 * y1)) - (l32 * y2)) / l33;
+  const double x3 = y3 / l33;
+  const double x2 = (y2 - (l32 * x3)) / l22;
+  const double x1 = ((y1 - (l21 * x2)) - (l31 * x3)) / l11;
+  if (!isfinite(x1) || !isfinite(x2) || !isfinite(x3)) return 0;
+  const double u = 0.5 * x3;
+  const double uu = u * u;
+  const double den = 1.0 + uu;
+  step[0] = (float)((1.0 - uu) / den);
+  step[1] = (float)((u + u) / den);
+  step[2] = (float)x1;
+  step[3] = (float)x2;
+  return 1;
+}
+
 /* final = step * final on the (c, s, tx, ty) parametrisation of the Matrix4f product (A.3-6) */
 static void compose(const float st[4], float fin[4]) {
   const float c = st[0], s = st[1], ms = -st[1];
@@ -359,14 +456,26 @@ void orc_icp(const float *src, int ns, const float *tgt, int nt, const float gue
       status |= DPGICP_STOP_NO_CORRESPONDENCES;
       break;
     }
-    moments_t m;
-    accumulate_moments(cur, tgt, ns, corr, d2, &m);
     float st[4];
-    solve_rigid_p2p(&m, st);
+    double sd2;
+    if (p->metric == DPGICP_METRIC_POINT_TO_LINE) {
+      normal_eq_t ne;
+      accumulate_normal_eq(cur, tgt, ns, nt, corr, d2, gate_threshold(p), &ne);
+      if (!solve_rigid_p2l(&ne, st)) {
+        status |= DPGICP_STOP_DEGENERATE;
+        break;
+      }
+      sd2 = (double)ne.sd2;
+    } else {
+      moments_t m;
+      accumulate_moments(cur, tgt, ns, corr, d2, &m);
+      solve_rigid_p2p(&m, st);
+      sd2 = (double)m.sd2;
+    }
     orc_transform_points(st, cur, ns, cur);        /* A.3-6 */
     compose(st, fin);
     out->iterations++;
-    out->mse = ((double)m.sd2 * (1.0 / SCALE_D2)) / (double)m.k;
+    out->mse = (sd2 * (1.0 / SCALE_D2)) / (double)K;
 
     /* A.5 DefaultConvergenceCriteria, in PCL's order */
     if (out->iterations >= p->max_iterations) {

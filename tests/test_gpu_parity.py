@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from dpg_slam_b200 import _abi, synth
-from dpg_slam_b200._abi import (COV_CENSI_CORR, COV_CENSI_INDEXPAIR, COV_REFERENCE_LIVE, FLAG_CONVERGED,
+from dpg_slam_b200._abi import (METRIC_POINT_TO_LINE, STOP_DEGENERATE, COV_CENSI_CORR, COV_CENSI_INDEXPAIR, COV_REFERENCE_LIVE, FLAG_CONVERGED,
                                 FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT, SEARCH_BRUTE, SEARCH_PRUNED, STOP_ITERATIONS,
                                 STOP_MASK, STOP_NO_CORRESPONDENCES, Params)
 from dpg_slam_b200.scanmatch import DpgIcpError
@@ -175,6 +175,42 @@ def test_non_reciprocal_and_iteration_limits(gpu_matcher):
         got, ref, _, _ = run_both(gpu_matcher, wl, p)
         assert_records_match(got, ref, str(kw))
     assert np.all(got["iterations"] >= 1)
+
+
+# ---- point-to-line metric (north-star extension; oracle-defined) ----------------------------------------------
+@pytest.mark.parametrize("search", [SEARCH_BRUTE, SEARCH_PRUNED])
+def test_point_to_line_batches(gpu_matcher, search):
+    for wl, div in ((synth.config_corridor(n_pairs=64, seed=2), 1), (synth.config_loop_closure(n_pairs=200, n_scans=80, seed=3), 1),
+                    (synth.config_loop_closure(n_pairs=64, n_scans=80, seed=3), 5)):
+        p = Params.defaults(downsample_divisor=div, cov_mode=COV_CENSI_CORR, metric=METRIC_POINT_TO_LINE, search=search)
+        got, ref, _, _ = run_both(gpu_matcher, wl, p)
+        assert_records_match(got, ref, f"p2l {wl.name} d{div} s{search}")
+    assert (got["status"] & FLAG_CONVERGED).mean() > 0.9
+
+
+def test_point_to_line_dense_4096(gpu_matcher):
+    """BASELINE config 4 shape: 4096 beams/scan, point-to-line."""
+    wl = synth.config_loop_closure(n_pairs=16, n_scans=24, n_beams=4096, seed=4)
+    p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR, metric=METRIC_POINT_TO_LINE)
+    got, ref, _, _ = run_both(gpu_matcher, wl, p)
+    assert_records_match(got, ref, "p2l dense")
+
+
+def test_point_to_line_degenerate_and_ragged(gpu_matcher):
+    x = np.linspace(-3, 3, 200, dtype=np.float32)
+    wall = np.stack([x, np.full_like(x, 2.0)], 1)
+    p = Params.defaults(downsample_divisor=1, metric=METRIC_POINT_TO_LINE, cov_mode=COV_CENSI_CORR)
+    gpu_matcher.upload_scans(np.concatenate([wall, wall]), np.array([0, 200, 400]))
+    got = gpu_matcher.submit_pairs([1], [0], [[0.0, 0.05, 0.0]], p)
+    ref = O.run_pair(wall, wall, [0.0, 0.05, 0.0], p)
+    assert got["status"][0] == ref.status and (got["status"][0] & STOP_MASK) == STOP_DEGENERATE
+    assert (got["tx"][0], got["ty"][0], got["iterations"][0]) == (ref.tx, ref.ty, ref.iterations)
+    wl = synth.config_corridor(n_pairs=8, n_beams=721, seed=12)
+    wl.ranges[2, :] = 40.0
+    wl.ranges[4, 2:] = 40.0
+    wl.ranges[6, ::2] = 40.0
+    got, ref, _, _ = run_both(gpu_matcher, wl, p)
+    assert_records_match(got, ref, "p2l ragged")
 
 
 # ---- edge cases ------------------------------------------------------------------------------------------------

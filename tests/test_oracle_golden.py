@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from dpg_slam_b200 import synth
-from dpg_slam_b200._abi import (COV_CENSI_CORR, COV_CENSI_INDEXPAIR, COV_REFERENCE_LIVE, FLAG_CONVERGED,
+from dpg_slam_b200._abi import (METRIC_POINT_TO_LINE, STOP_DEGENERATE, COV_CENSI_CORR, COV_CENSI_INDEXPAIR, COV_REFERENCE_LIVE, FLAG_CONVERGED,
                                 FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT, STOP_ITERATIONS, STOP_MASK,
                                 STOP_NO_CORRESPONDENCES, Params)
 from oracle import oracle_py as O
@@ -222,3 +222,46 @@ def test_enumerate_pairs_matches_reference_loop_order():
             if d <= (5.0 if ps[j] == ps[i] else 2.0):
                 want.append((i, j))
     assert list(zip(src.tolist(), tgt.tolist())) == want
+
+
+# ---- point-to-line metric (north-star extension; the oracle is its definition) ---------------------------
+def test_point_to_line_converges_faster_and_closer():
+    wl = synth.config_loop_closure(n_pairs=40, n_scans=40, seed=3)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    p2p = Params.defaults(downsample_divisor=1)
+    p2l = p2p.copy(metric=METRIC_POINT_TO_LINE)
+    a, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, p2p, fast=1)
+    b, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, p2l, fast=1)
+    assert np.all(b["status"] & FLAG_CONVERGED)
+    assert b["iterations"].mean() < 0.6 * a["iterations"].mean()
+    err = lambda r: np.median(np.hypot(r["tx"] - wl.truth[:, 0], r["ty"] - wl.truth[:, 1]))
+    assert err(b) < err(a)
+    c, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, p2l, fast=0)
+    assert b.tobytes() == c.tobytes()                         # grid search == brute force for this metric too
+
+
+def test_point_to_line_degenerate_geometry_is_flagged():
+    # a single straight wall: sliding along it is unobservable -> normal equations singular
+    x = np.linspace(-3, 3, 200, dtype=np.float32)
+    wall = np.stack([x, np.full_like(x, 2.0)], 1)
+    p = Params.defaults(downsample_divisor=1, metric=METRIC_POINT_TO_LINE)
+    res = O.run_pair(wall, wall, [0.0, 0.05, 0.0], p)
+    assert res.status & STOP_MASK == STOP_DEGENERATE and not res.status & FLAG_CONVERGED
+    # the same wall plus a perpendicular one is well posed
+    y = np.linspace(-1, 2, 100, dtype=np.float32)
+    corner = np.concatenate([wall, np.stack([np.full_like(y, 3.0), y], 1)])
+    res = O.run_pair(corner, corner, [0.03, 0.05, 0.01], p)
+    assert res.status & FLAG_CONVERGED and abs(res.tx) < 1e-3 and abs(res.ty) < 1e-3 and abs(res.theta) < 1e-3
+
+
+def test_point_to_line_isolated_points_fall_back_to_point_rows():
+    # targets farther apart than the gate: no usable segment, every row is a point row -> well posed
+    rng = np.random.default_rng(1)
+    tgt = (rng.uniform(-20, 20, (60, 2))).astype(np.float32)
+    th = 0.01
+    R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    src = ((tgt - np.array([0.05, -0.03])) @ R).astype(np.float32)
+    p = Params.defaults(downsample_divisor=1, metric=METRIC_POINT_TO_LINE)
+    res = O.run_pair(src, tgt, [0, 0, 0], p)
+    assert res.status & FLAG_CONVERGED and res.n_correspondences == 60
+    assert abs(res.theta - th) < 1e-4
