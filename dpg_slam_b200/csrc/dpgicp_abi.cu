@@ -55,7 +55,8 @@ struct dpgicp_ctx {
   DevBuf stage, offsets, misc, corr;
   DevBuf state[2], susp[2];                  /* suspended-pair state slots + pair lists, ping-pong between stages */
   unsigned long long *d_queue = nullptr;     /* [0..2] stage queue heads, [4],[5] suspended counts, [8..15] counters */
-  int max_stages = 3;
+  int max_stages = 4;
+  std::vector<int> chain;                    /* DPGICP_CHAIN: target warps per stage (development knob) */
   int *d_bad = nullptr;
   int force_warps = 0;
   int force_ctas_per_sm = 0;
@@ -120,11 +121,11 @@ float gate_threshold(const dpgicp_params *p) {
 }
 
 template <int WARPS, bool PRUNED>
-int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t max_items, int *grid_out) {
+int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t max_items, int nw, int *grid_out) {
   auto kern = icp_pairs_kernel<WARPS, PRUNED>;
   CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+  CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nw * 32, smem));
   if (per_sm < 1) return fail(ctx, DPGICP_E_TOOBIG, "scan too large for one CTA's shared memory");
   if (ctx->force_ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->force_ctas_per_sm);
   /* persistent grid: a whole number of resident CTAs per SM, never more CTAs than work items */
@@ -135,25 +136,33 @@ int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t m
     if (*grid_out < 0) { *grid_out = (int)grid; return DPGICP_OK; }      /* query only */
     *grid_out = (int)grid;
   }
-  kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(kp);
+  kern<<<(unsigned)grid, nw * 32, smem, ctx->stream>>>(kp);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   return DPGICP_OK;
 }
 
+/* nw warps per CTA run on the instantiation with the next power-of-two register budget */
 template <bool PRUNED>
-int launch_icp_w(dpgicp_ctx *ctx, int warps, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
-  switch (warps) {
-    case 1: return launch_icp_t<1, PRUNED>(ctx, kp, smem, n, grid_out);
-    case 2: return launch_icp_t<2, PRUNED>(ctx, kp, smem, n, grid_out);
-    case 4: return launch_icp_t<4, PRUNED>(ctx, kp, smem, n, grid_out);
-    case 8: return launch_icp_t<8, PRUNED>(ctx, kp, smem, n, grid_out);
-    default: return launch_icp_t<16, PRUNED>(ctx, kp, smem, n, grid_out);
-  }
+int launch_icp_w(dpgicp_ctx *ctx, int nw, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
+  if (nw <= 1) return launch_icp_t<1, PRUNED>(ctx, kp, smem, n, 1, grid_out);
+  if (nw <= 2) return launch_icp_t<2, PRUNED>(ctx, kp, smem, n, nw, grid_out);
+  if (nw <= 4) return launch_icp_t<4, PRUNED>(ctx, kp, smem, n, nw, grid_out);
+  if (nw <= 8) return launch_icp_t<8, PRUNED>(ctx, kp, smem, n, nw, grid_out);
+  if (nw <= 16) return launch_icp_t<16, PRUNED>(ctx, kp, smem, n, nw, grid_out);
+  return launch_icp_t<32, PRUNED>(ctx, kp, smem, n, std::min(nw, 32), grid_out);
 }
 
-int launch_stage(dpgicp_ctx *ctx, bool pruned, int warps, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
-  return pruned ? launch_icp_w<true>(ctx, warps, kp, smem, n, grid_out) : launch_icp_w<false>(ctx, warps, kp, smem, n, grid_out);
+int launch_stage(dpgicp_ctx *ctx, bool pruned, int nw, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
+  return pruned ? launch_icp_w<true>(ctx, nw, kp, smem, n, grid_out) : launch_icp_w<false>(ctx, nw, kp, smem, n, grid_out);
+}
+
+/* warps per CTA close to `target` that split `tiles` 32-point tiles evenly (every warp gets
+ * ceil(tiles / nw) or one fewer): 34 tiles -> 4, 7, 12, 17 for targets 4, 8, 16, 32 */
+int balanced_warps(int tiles, int target) {
+  target = std::max(1, std::min(32, target));
+  const int per_warp = (tiles + target - 1) / target;
+  return std::max(1, (tiles + per_warp - 1) / per_warp);
 }
 
 int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_params *p, int32_t *corr_out,
@@ -190,18 +199,24 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   const size_t smem = smem_bytes(n_cap);
   const bool pruned = p->search == DPGICP_SEARCH_PRUNED;
 
-  /* stage widths (warps per pair): narrow for the bulk, wider for the pairs still running when a
-   * stage's queue runs dry; never more warps than the pair has 32-point tiles */
+  /* stage widths (warps per pair): narrow CTAs for the bulk of the batch, wider ones for the pairs
+   * still running when a stage's queue runs dry; each width is balanced against the tile count */
   const int tiles = n_cap / kTile;
   int w0 = ctx->force_warps;
   if (w0 <= 0) w0 = n_cap <= 512 ? 2 : (n_cap <= 2048 ? 4 : 8);
-  int widths[3] = {w0, w0, w0};
+  int targets[4] = {w0, 2 * w0, 16, 16};       /* measured on B200: 34 tiles -> 4, 7, 12 warps; a 17-warp CTA (64 registers
+                                                * per thread) is no faster per pass than 12 warps                         */
+  int n_targets = 3;
+  if (!ctx->chain.empty()) {
+    n_targets = 0;
+    for (int w : ctx->chain) if (n_targets < 4) targets[n_targets++] = w;
+  }
+  int widths[4] = {balanced_warps(tiles, targets[0]), 0, 0, 0};
   int n_stages = 1;
   if (corr_out == nullptr) {
-    for (int k = 1; k < ctx->max_stages; ++k) {
-      int w = std::min(16, widths[n_stages - 1] * 2);
-      while (w > 1 && w > tiles) w >>= 1;
-      if (w <= widths[n_stages - 1]) break;
+    for (int k = 1; k < n_targets && n_stages < ctx->max_stages; ++k) {
+      const int w = balanced_warps(tiles, targets[k]);
+      if (w <= widths[n_stages - 1]) continue;
       widths[n_stages++] = w;
     }
   }
@@ -413,7 +428,14 @@ int dpgicp_create(int device, dpgicp_ctx **out) {
   }
   if (const char *w = std::getenv("DPGICP_WARPS")) ctx->force_warps = std::atoi(w);
   if (const char *c = std::getenv("DPGICP_CTAS_PER_SM")) ctx->force_ctas_per_sm = std::atoi(c);
-  if (const char *c = std::getenv("DPGICP_STAGES")) ctx->max_stages = std::max(1, std::min(3, std::atoi(c)));
+  if (const char *c = std::getenv("DPGICP_STAGES")) ctx->max_stages = std::max(1, std::min(4, std::atoi(c)));
+  if (const char *c = std::getenv("DPGICP_CHAIN")) {
+    for (const char *q = c; *q;) {
+      ctx->chain.push_back(std::max(1, std::atoi(q)));
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+  }
   *out = ctx;
   return DPGICP_OK;
 }

@@ -43,7 +43,9 @@ constexpr float kPad   = 1.0e30f;   /* coordinate of padded slots: any d2 agains
 constexpr double kScaleLin  = 4294967296.0;      /* 2^32 */
 constexpr double kScaleProd = 268435456.0;       /* 2^28 */
 constexpr double kScaleD2   = 1099511627776.0;   /* 2^40 */
-constexpr int   kMaxWarps = 16;
+constexpr int   kMaxWarps = 32;
+constexpr int   kCovChunk = 16;  /* tile partials per covariance reduction round: FIXED, the summation order must not
+                                  * depend on the CTA width                                                         */
 constexpr int   kStateHeader = 64;  /* bytes of scalars in front of a suspended pair's arrays      */
 
 struct PairTask {            /* 24 bytes: pair indices + the guess as matrix entries (host libm) */
@@ -467,21 +469,23 @@ __device__ __forceinline__ void block_sum11(double *acc, double *dpart, double *
  * Rigid steps (thread 0 of the CTA), mirroring oracle/dpg_oracle.c operation for operation.
  * red[0..8] = nine exact fixed-point sums (meaning depends on the metric), red[9] = sum d2, red[10] = K
  * ---------------------------------------------------------------------------------------------- */
-/* point-to-point: planar Procrustes in binary64 (PCL TransformationEstimationSVD on z = 0 data) */
-__device__ __forceinline__ void solve_p2p(const long long *red, double Kd, float st[4]) {
+/* point-to-point: planar Procrustes in binary64 (PCL TransformationEstimationSVD on z = 0 data).
+ * Division by K and by the norm are multiplications by one reciprocal each, so the dependent chain is
+ * reciprocal(K) || sums -> sqrt -> reciprocal -> products (this runs on one thread per pass). */
+__device__ __forceinline__ void solve_p2p(const long long *red, double invK, float st[4]) {
   const double spx = __dmul_rn((double)red[0], 1.0 / kScaleLin);
   const double spy = __dmul_rn((double)red[1], 1.0 / kScaleLin);
   const double sqx = __dmul_rn((double)red[2], 1.0 / kScaleLin);
   const double sqy = __dmul_rn((double)red[3], 1.0 / kScaleLin);
   const double dot = __dmul_rn((double)(red[4] + red[7]), 1.0 / kScaleProd);
   const double crs = __dmul_rn((double)(red[5] - red[6]), 1.0 / kScaleProd);
-  const double a = __dsub_rn(dot, __ddiv_rn(__dadd_rn(__dmul_rn(spx, sqx), __dmul_rn(spy, sqy)), Kd));
-  const double b = __dsub_rn(crs, __ddiv_rn(__dsub_rn(__dmul_rn(spx, sqy), __dmul_rn(spy, sqx)), Kd));
+  const double a = __dsub_rn(dot, __dmul_rn(__dadd_rn(__dmul_rn(spx, sqx), __dmul_rn(spy, sqy)), invK));
+  const double b = __dsub_rn(crs, __dmul_rn(__dsub_rn(__dmul_rn(spx, sqy), __dmul_rn(spy, sqx)), invK));
   const double h = __dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
   double c = 1.0, s = 0.0;
-  if (h > 0.0) { c = __ddiv_rn(a, h); s = __ddiv_rn(b, h); }
-  const double mpx = __ddiv_rn(spx, Kd), mpy = __ddiv_rn(spy, Kd);
-  const double mqx = __ddiv_rn(sqx, Kd), mqy = __ddiv_rn(sqy, Kd);
+  if (h > 0.0) { const double rh = __ddiv_rn(1.0, h); c = __dmul_rn(a, rh); s = __dmul_rn(b, rh); }
+  const double mpx = __dmul_rn(spx, invK), mpy = __dmul_rn(spy, invK);
+  const double mqx = __dmul_rn(sqx, invK), mqy = __dmul_rn(sqy, invK);
   const double tx = __dsub_rn(mqx, __dsub_rn(__dmul_rn(c, mpx), __dmul_rn(s, mpy)));
   const double ty = __dsub_rn(mqy, __dadd_rn(__dmul_rn(s, mpx), __dmul_rn(c, mpy)));
   st[0] = (float)c; st[1] = (float)s; st[2] = (float)tx; st[3] = (float)ty;
@@ -552,6 +556,9 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SmemLayout L = carve(smem_raw, P.n_cap);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nw = blockDim.x >> 5;            /* warps of this CTA: <= WARPS, chosen by the host so that
+                                              * the pair's tiles divide evenly among them            */
+  const int nthreads = blockDim.x;
   const int div = P.divisor;
   constexpr int GPT = kTile / kGroup;        /* groups per tile */
   uint32_t mbar_phase = 0;
@@ -600,21 +607,21 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         if (bs) bulk_g2s(L.src, P.resume ? (const void *)(slot_in + kStateHeader) : (const void *)srow, bs, L.mbar);
         if (bn) bulk_g2s(L.nn, slot_in + kStateHeader + (size_t)P.n_cap * 8, bn, L.mbar);
       }
-      if (!tma_t) for (int k = tid; k < nt; k += WARPS * 32) L.tgt[k] = __ldg(trow + (size_t)k * div);
-      if (!tma_s) for (int k = tid; k < ns; k += WARPS * 32) L.src[k] = __ldg(srow + (size_t)k * div);
+      if (!tma_t) for (int k = tid; k < nt; k += nthreads) L.tgt[k] = __ldg(trow + (size_t)k * div);
+      if (!tma_s) for (int k = tid; k < ns; k += nthreads) L.src[k] = __ldg(srow + (size_t)k * div);
       mbar_wait(L.mbar, mbar_phase);
       mbar_phase ^= 1u;
     }
     __syncthreads();
     /* pad to whole tiles, apply the guess (PCL transformCloud(input, guess), App. A.2), boxes */
-    for (int k = nt + tid; k < tt * kTile; k += WARPS * 32) L.tgt[k] = make_float2(kPad, kPad);
-    for (int k = ns + tid; k < ts * kTile; k += WARPS * 32) L.src[k] = make_float2(kPad, kPad);
+    for (int k = nt + tid; k < tt * kTile; k += nthreads) L.tgt[k] = make_float2(kPad, kPad);
+    for (int k = ns + tid; k < ts * kTile; k += nthreads) L.src[k] = make_float2(kPad, kPad);
     __syncthreads();
-    for (int t = warp; t < tt; t += WARPS) {
+    for (int t = warp; t < tt; t += nw) {
       const int k = t * kTile + lane;
       store_tile_boxes(L.tgt[k], k < nt, t, L.tbox, nullptr);
     }
-    for (int t = warp; t < ts; t += WARPS) {
+    for (int t = warp; t < ts; t += nw) {
       const int k = t * kTile + lane;
       float2 p = L.src[k];
       if (!P.resume) {
@@ -628,7 +635,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
 
     /* ---- parity hook: a single correspondence pass ------------------------------------------ */
     if (P.corr_out != nullptr) {
-      for (int tile = warp; tile < ts; tile += WARPS) {
+      for (int tile = warp; tile < ts; tile += nw) {
         float2 q; int j; float d; bool fwd;
         const bool acc = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
                                             stats);
@@ -657,7 +664,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
     for (;;) {
       long long m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, m6 = 0, m7 = 0, m8 = 0, m_d2 = 0;
       int m_k = 0;
-      for (int tile = warp; tile < ts; tile += WARPS) {
+      for (int tile = warp; tile < ts; tile += nw) {
         float2 q; int j; float d; bool fwd;
         const bool acc = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
                                             stats);
@@ -750,8 +757,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           status |= DPGICP_STOP_DEGENERATE;            /* geometry does not constrain the pose */
           st = 2;
         } else {
-          const double Kd = (double)K;
-          if (P.metric != DPGICP_METRIC_POINT_TO_LINE) solve_p2p(L.red, Kd, stp);
+          const double invK = __ddiv_rn(1.0, (double)K);
+          if (P.metric != DPGICP_METRIC_POINT_TO_LINE) solve_p2p(L.red, invK, stp);
           const float sc = stp[0], ss = stp[1], stx = stp[2], sty = stp[3];
           L.step[0] = sc; L.step[1] = ss; L.step[2] = stx; L.step[3] = sty;
           /* final = step * final (App. A.3-6) */
@@ -761,7 +768,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           const float nty = __fadd_rn(__fadd_rn(__fmul_rn(ss, ftx), __fmul_rn(sc, fty)), sty);
           fc = nc; fs = nsn; ftx = ntx; fty = nty;
           ++iterations;
-          mse = __ddiv_rn(__dmul_rn((double)L.red[9], 1.0 / kScaleD2), Kd);
+          mse = __dmul_rn(__dmul_rn((double)L.red[9], 1.0 / kScaleD2), invK);
           /* DefaultConvergenceCriteria (App. A.5), in PCL's order */
           const float tr = __fsub_rn(__fadd_rn(__fadd_rn(sc, sc), 1.0f), 1.0f);
           const double cos_angle = __dmul_rn(0.5, (double)tr);
@@ -793,7 +800,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       /* src' = step * src' in place (App. A.3-6) and refresh the source boxes */
       {
         const float sc = L.step[0], ss = L.step[1], stx = L.step[2], sty = L.step[3];
-        for (int t = warp; t < ts; t += WARPS) {
+        for (int t = warp; t < ts; t += nw) {
           const int k = t * kTile + lane;
           float2 p = L.src[k];
           if (k < ns) { p = xform(sc, ss, stx, sty, p); L.src[k] = p; }
@@ -810,7 +817,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       unsigned char *slot = P.state_out + (size_t)(uint32_t)L.ctl[4] * (size_t)P.slot_bytes;
       float2 *s_src = reinterpret_cast<float2 *>(slot + kStateHeader);
       int32_t *s_nn = reinterpret_cast<int32_t *>(slot + kStateHeader + (size_t)P.n_cap * 8);
-      for (int k = tid; k < ns; k += WARPS * 32) { s_src[k] = L.src[k]; s_nn[k] = L.nn[k]; }
+      for (int k = tid; k < ns; k += nthreads) { s_src[k] = L.src[k]; s_nn[k] = L.nn[k]; }
       if (tid == 0) {
         SuspHeader h;
         h.fc = fc; h.fs = fs; h.ftx = ftx; h.fty = fty; h.mse = mse; h.mse_prev = mse_prev;
@@ -846,7 +853,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       } else {
         /* CENSI_CORR: correspondences at the final pose: src'' = final * src (original points) */
         __syncthreads();
-        for (int t = warp; t < ts; t += WARPS) {
+        for (int t = warp; t < ts; t += nw) {
           const int k = t * kTile + lane;
           float2 p = make_float2(kPad, kPad);
           if (k < ns) { p = xform(Tc, Ts, Ttx, Tty, __ldg(srow + (size_t)k * div)); }
@@ -854,7 +861,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
         }
         __syncthreads();
-        for (int tile = warp; tile < ts; tile += WARPS) {
+        for (int tile = warp; tile < ts; tile += nw) {
           float2 q; int j; float d; bool fwd;
           const bool ok = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
                                              stats);
@@ -867,9 +874,9 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         n_cov = ns;
       }
       const int cov_tiles = (n_cov + kTile - 1) / kTile;
-      for (int chunk = 0; chunk < cov_tiles; chunk += kMaxWarps) {
-        const int chunk_end = chunk + kMaxWarps < cov_tiles ? chunk + kMaxWarps : cov_tiles;
-        for (int tile = chunk + warp; tile < chunk_end; tile += WARPS) {
+      for (int chunk = 0; chunk < cov_tiles; chunk += kCovChunk) {
+        const int chunk_end = chunk + kCovChunk < cov_tiles ? chunk + kCovChunk : cov_tiles;
+        for (int tile = chunk + warp; tile < chunk_end; tile += nw) {
           double acc[11];
 #pragma unroll
           for (int k = 0; k < 11; ++k) acc[k] = 0.0;

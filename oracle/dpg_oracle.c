@@ -297,19 +297,22 @@ static void accumulate_moments(const float *src_t, const float *tgt, int ns,
 /* PCL TransformationEstimationSVD on z = 0 data == planar Procrustes (Appendix A.3-5, A.6).
  * step = (c, s, tx, ty) in binary32. */
 static void solve_rigid_p2p(const moments_t *m, float step[4]) {
-  const double K = (double)m->k;
+  /* divisions by K and by the norm are multiplications by one reciprocal each (a short dependent
+   * chain: this runs on one GPU thread per pass); the difference from exact division is a few
+   * binary64 ulps, far below the binary32 rounding of the step entries */
+  const double invK = 1.0 / (double)m->k;
   const double spx = (double)m->spx * (1.0 / SCALE_LIN);
   const double spy = (double)m->spy * (1.0 / SCALE_LIN);
   const double sqx = (double)m->sqx * (1.0 / SCALE_LIN);
   const double sqy = (double)m->sqy * (1.0 / SCALE_LIN);
   const double dot = (double)(m->sxx + m->syy) * (1.0 / SCALE_PROD);
   const double crs = (double)(m->sxy - m->syx) * (1.0 / SCALE_PROD);
-  const double a = dot - ((spx * sqx) + (spy * sqy)) / K;
-  const double b = crs - ((spx * sqy) - (spy * sqx)) / K;
+  const double a = dot - (((spx * sqx) + (spy * sqy)) * invK);
+  const double b = crs - (((spx * sqy) - (spy * sqx)) * invK);
   const double h = sqrt((a * a) + (b * b));
   double c = 1.0, s = 0.0;
-  if (h > 0.0) { c = a / h; s = b / h; }
-  const double mpx = spx / K, mpy = spy / K, mqx = sqx / K, mqy = sqy / K;
+  if (h > 0.0) { const double rh = 1.0 / h; c = a * rh; s = b * rh; }
+  const double mpx = spx * invK, mpy = spy * invK, mqx = sqx * invK, mqy = sqy * invK;
   const double tx = mqx - ((c * mpx) - (s * mpy));
   const double ty = mqy - ((s * mpx) + (c * mpy));
   step[0] = (float)c;
@@ -475,7 +478,7 @@ void orc_icp(const float *src, int ns, const float *tgt, int nt, const float gue
     orc_transform_points(st, cur, ns, cur);        /* A.3-6 */
     compose(st, fin);
     out->iterations++;
-    out->mse = (sd2 * (1.0 / SCALE_D2)) / (double)K;
+    out->mse = (sd2 * (1.0 / SCALE_D2)) * (1.0 / (double)K);
 
     /* A.5 DefaultConvergenceCriteria, in PCL's order */
     if (out->iterations >= p->max_iterations) {

@@ -359,9 +359,14 @@ def test_staged_chain_equals_single_stage(gpu_matcher, monkeypatch):
     p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR)
     gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
     want = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
-    for stages, warps in ((1, 4), (2, 2), (3, 1), (3, 8), (1, 16)):
+    for stages, warps, chain in ((1, 4, None), (2, 2, None), (3, 1, None), (3, 8, None), (1, 16, None), (4, 0, "3,5,11,32"),
+                                 (4, 0, "4,8,16,32"), (2, 0, "1,32"), (1, 32, None)):
         monkeypatch.setenv("DPGICP_STAGES", str(stages))
         monkeypatch.setenv("DPGICP_WARPS", str(warps))
+        if chain:
+            monkeypatch.setenv("DPGICP_CHAIN", chain)
+        else:
+            monkeypatch.delenv("DPGICP_CHAIN", raising=False)
         with ScanMatcher(0) as sm:
             sm.upload_ranges(wl.ranges, wl.scanner)
             got = sm.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
@@ -371,6 +376,7 @@ def test_staged_chain_equals_single_stage(gpu_matcher, monkeypatch):
     # down-sampled clouds take the gather path when fresh and the contiguous path when resumed
     p5 = p.copy(downsample_divisor=5)
     want5 = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p5)
+    monkeypatch.delenv("DPGICP_CHAIN", raising=False)
     monkeypatch.setenv("DPGICP_STAGES", "1")
     monkeypatch.setenv("DPGICP_WARPS", "2")
     with ScanMatcher(0) as sm:

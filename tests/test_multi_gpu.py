@@ -1,0 +1,71 @@
+"""GPU, needs >= 2 devices (skipped on a 1-GPU box): the sharded path over NCCL gives, on every rank, the
+same records bit for bit as one GPU running the whole batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_pairs, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from dpg_slam_b200 import sharded, synth
+        from dpg_slam_b200._abi import COV_CENSI_CORR, Params
+        from dpg_slam_b200.scanmatch import ScanMatcher
+        wl = synth.config_loop_closure(n_pairs=n_pairs, n_scans=200, seed=31)
+        p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR)
+        stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(stream), ScanMatcher(rank) as sm:
+            sm.set_stream(stream.cuda_stream)
+            sm.upload_ranges(wl.ranges, wl.scanner)                 # scan store replicated on every GPU
+            sh = sharded.ShardedScanMatcher(sm, rank, world, None, dev)
+            sh.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)          # pair k -> rank k % world
+            sh.run(p)
+            allrec = sh.gather()
+            single = None
+            if rank == 0:
+                sm.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
+                sm.run(p)
+                single = sm.fetch_results()
+        ok = True if single is None else allrec.tobytes() == single.tobytes()
+        q.put((rank, ok, len(allrec), int(allrec["iterations"].sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_nccl_equals_single_gpu():
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n_pairs = 1001                                                  # not a multiple of the world size
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_pairs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert all(ok and n == n_pairs for _, ok, n, _ in got)
+    assert len({s for _, _, _, s in got}) == 1                      # every rank holds the same gathered batch

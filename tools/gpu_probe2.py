@@ -10,12 +10,13 @@ from dpg_slam_b200.scanmatch import ScanMatcher
 from gpu_probe import time_run
 
 which, n_pairs = sys.argv[1], int(sys.argv[2])
-settings = [tuple(int(x) for x in s.split(",")) for s in sys.argv[3:]] or [(3, 0, 0), (1, 0, 0)]
+chains = [a for a in sys.argv[3:]] or ["4,8,32"]
 wl = synth.config_corridor(n_pairs=n_pairs, seed=2) if which == "corridor" else synth.config_loop_closure(n_pairs=n_pairs, n_scans=2000, seed=3)
 tag = os.path.basename(os.environ.get("DPGICP_LIBRARY", "default")).replace(".so", "")
 out = {}
-for stages, warps, ctas in settings:
-    os.environ["DPGICP_STAGES"], os.environ["DPGICP_WARPS"], os.environ["DPGICP_CTAS_PER_SM"] = str(stages), str(warps), str(ctas)
+for chain in chains:
+    os.environ["DPGICP_CHAIN"] = chain
+    stages, warps, ctas = chain.replace(",", "-"), 0, 0
     with ScanMatcher(0) as sm:
         sm.upload_ranges(wl.ranges, wl.scanner)
         sm.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
