@@ -338,13 +338,17 @@ def run_product(args):
     nominal = 148 * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
     measured = probe["mul_add_ops_per_s"] / 1e12
     peak = measured if measured > 0 else nominal
-    traffic = None
+    traffic, ncu_inst = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_icp_kernel_ncu.json"))).get("dram_bytes_per_launch")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_icp_kernel_ncu.json")))
+        if WORKLOAD == "corridor":       # the capture is of this workload's launch
+            traffic = prof.get("dram_bytes_per_launch")
+            ncu_inst = prof.get("instructions_executed")
     except Exception:
         pass
     alg_bytes = float(np.sum(8.0 * (ns + nt) + 20 + 112))
-    roofline = {"kernel": "dpg::icp_pairs_kernel<WARPS,PRUNED> (persistent, one launch per step)",
+    roofline = {"kernel": "dpg::icp_pairs_kernel<WARPS,PRUNED> (persistent CTAs; one step = a chain of up to 3 launches with "
+                          "growing warps per pair, timed together)",
                 "bound": "fp32", "achieved": alg_tflops, "peak": peak, "unit": "TFLOP/s", "frac": alg_tflops / peak,
                 "peak_source": "measured on this GPU in this run by dpgicp_fp32_probe: separately rounded FMUL+FADD "
                                "(the bit-exact distance loop may not use FMA); MEASURED_PEAKS.json has no FP32 figure; "
@@ -357,6 +361,12 @@ def run_product(args):
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs"), "frac": (alg_bytes / (k_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
                 "fp32_probe_tops": {"mul_add": measured, "fma": probe["fma_ops_per_s"] / 1e12}}
+    if ncu_inst:
+        # issue-slot view: warp instructions of one step (ncu capture of this same workload, profiles/) over the
+        # live kernel time, against 4 schedulers x 148 SMs x SM clock
+        issue_peak = 4.0 * 148 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        roofline["issue"] = {"warp_instructions_per_step": ncu_inst, "achieved_ginst_s": ncu_inst / (k_ms * 1e-3) / 1e9,
+                             "peak_ginst_s": issue_peak / 1e9, "frac": ncu_inst / (k_ms * 1e-3) / issue_peak}
 
     # ---------------- CPU baseline on this box's host cores (bounded sample; N = 1 only) ----------------
     cpu = None

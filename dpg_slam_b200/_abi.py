@@ -20,7 +20,7 @@ SEARCH_BRUTE, SEARCH_PRUNED = 0, 1
 COV_REFERENCE_LIVE, COV_CENSI_INDEXPAIR, COV_CENSI_CORR = 0, 1, 2
 STOP_MASK = 0xFF
 STOP_NONE, STOP_ITERATIONS, STOP_TRANSFORM, STOP_ABS_MSE, STOP_NO_CORRESPONDENCES, STOP_DEGENERATE = 0, 1, 2, 3, 4, 5
-FLAG_CONVERGED, FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT = 0x100, 0x200, 0x400
+FLAG_CONVERGED, FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT, FLAG_FACTOR_INVALID = 0x100, 0x200, 0x400, 0x800
 MAX_ABS_COORD = 1000.0
 MAX_POINTS = 8192
 
@@ -88,14 +88,19 @@ RESULT_DTYPE = np.dtype([
     ("mse", "<f8"), ("cov", "<f8", (9,)),
 ], align=True)
 
-assert C.sizeof(Result) == 112 and RESULT_DTYPE.itemsize == 112
+FACTOR_DTYPE = np.dtype([
+    ("from_node", "<i4"), ("to_node", "<i4"), ("tx", "<f4"), ("ty", "<f4"), ("theta", "<f4"), ("status", "<u4"),
+    ("sqrt_info", "<f8", (9,)),
+], align=True)
+
+assert C.sizeof(Result) == 112 and RESULT_DTYPE.itemsize == 112 and FACTOR_DTYPE.itemsize == 96
 assert C.sizeof(Params) == 72
 
 EXPORTS = [
     "dpgicp_abi_version", "dpgicp_default_params", "dpgicp_create", "dpgicp_destroy",
     "dpgicp_last_error", "dpgicp_set_stream", "dpgicp_synchronize", "dpgicp_upload_scans",
     "dpgicp_upload_ranges", "dpgicp_scan_count", "dpgicp_download_scan", "dpgicp_submit_pairs",
-    "dpgicp_set_pairs", "dpgicp_run", "dpgicp_fetch_results", "dpgicp_results_device_ptr",
+    "dpgicp_set_pairs", "dpgicp_run", "dpgicp_fetch_results", "dpgicp_fetch_factors", "dpgicp_results_device_ptr",
     "dpgicp_last_run_counters", "dpgicp_single_pair", "dpgicp_cov", "dpgicp_correspondences",
     "dpgicp_enumerate_pairs", "dpgicp_relative_guess", "dpgicp_fp32_probe",
 ]
@@ -137,6 +142,7 @@ def load_library() -> C.CDLL:
         "dpgicp_set_pairs": (C.c_int, [vp, vp, vp, vp, i64]),
         "dpgicp_run": (C.c_int, [vp, PP]),
         "dpgicp_fetch_results": (C.c_int, [vp, vp, i64]),
+        "dpgicp_fetch_factors": (C.c_int, [vp, vp, i64]),
         "dpgicp_results_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "dpgicp_last_run_counters": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
         "dpgicp_single_pair": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, PR]),

@@ -566,6 +566,25 @@ int dpgicp_fetch_results(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n) {
   return DPGICP_OK;
 }
 
+int dpgicp_fetch_factors(dpgicp_ctx *ctx, dpgicp_factor *out, int64_t n) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n < 0 || n > ctx->batch.n_pairs || (n > 0 && !out)) return fail(ctx, DPGICP_E_INVALID, "bad fetch arguments");
+  if (n == 0) { CU_TRY(ctx, cudaStreamSynchronize(ctx->stream)); return DPGICP_OK; }
+  int rc;
+  if ((rc = reserve(ctx, ctx->stage, sizeof(dpgicp_factor) * (size_t)n))) return rc;
+  const int threads = 128;
+  const long long blocks = (n + threads - 1) / threads;
+  factors_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>((const dpgicp_result *)ctx->batch.results.p,
+                                                              (const PairTask *)ctx->batch.tasks.p, (long long)n,
+                                                              (dpgicp_factor *)ctx->stage.p);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaMemcpyAsync(out, ctx->stage.p, sizeof(dpgicp_factor) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
+}
+
 int dpgicp_results_device_ptr(dpgicp_ctx *ctx, void **out_ptr, int64_t *out_n) {
   if (!ctx || !out_ptr || !out_n) return DPGICP_E_INVALID;
   *out_ptr = ctx->batch.results.p;

@@ -1088,6 +1088,60 @@ __global__ void enumerate_fill_kernel(const float2 *xy, const int32_t *pass, int
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Records -> pose-graph factors (addObservationConstraint, dpg_slam.cc:331-338): information = cov^-1
+ * by cofactors, R = its upper Cholesky factor.  One thread per pair; HBM-bound (136 B in, 96 B out).
+ * Individually rounded binary64 operations, mirrored by oracle/dpg_oracle.c orc_factor.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void factors_kernel(const dpgicp_result *__restrict__ rec, const PairTask *__restrict__ tasks, long long n,
+                               dpgicp_factor *__restrict__ out) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const dpgicp_result r = rec[k];
+  dpgicp_factor f;
+  f.from_node = tasks[k].tgt; f.to_node = tasks[k].src;
+  f.tx = r.tx; f.ty = r.ty; f.theta = r.theta;
+  const double a = r.cov[0], b = r.cov[1], c = r.cov[2], d = r.cov[4], e = r.cov[5], g = r.cov[8];
+  /* information matrix by cofactors of the symmetric covariance */
+  const double c00 = __dsub_rn(__dmul_rn(d, g), __dmul_rn(e, e));
+  const double c01 = __dsub_rn(__dmul_rn(c, e), __dmul_rn(b, g));
+  const double c02 = __dsub_rn(__dmul_rn(b, e), __dmul_rn(c, d));
+  const double det = __dadd_rn(__dadd_rn(__dmul_rn(a, c00), __dmul_rn(b, c01)), __dmul_rn(c, c02));
+  bool ok = (det > 0.0) && isfinite(det);
+  double R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (ok) {
+    const double id = __ddiv_rn(1.0, det);
+    const double i00 = __dmul_rn(c00, id), i01 = __dmul_rn(c01, id), i02 = __dmul_rn(c02, id);
+    const double i11 = __dmul_rn(__dsub_rn(__dmul_rn(a, g), __dmul_rn(c, c)), id);
+    const double i12 = __dmul_rn(__dsub_rn(__dmul_rn(b, c), __dmul_rn(a, e)), id);
+    const double i22 = __dmul_rn(__dsub_rn(__dmul_rn(a, d), __dmul_rn(b, b)), id);
+    /* upper Cholesky: info = R^T R */
+    ok = i00 > 0.0;
+    if (ok) {
+      const double r00 = __dsqrt_rn(i00);
+      const double r01 = __ddiv_rn(i01, r00), r02 = __ddiv_rn(i02, r00);
+      const double p11 = __dsub_rn(i11, __dmul_rn(r01, r01));
+      ok = p11 > 0.0;
+      if (ok) {
+        const double r11 = __dsqrt_rn(p11);
+        const double r12 = __ddiv_rn(__dsub_rn(i12, __dmul_rn(r01, r02)), r11);
+        const double p22 = __dsub_rn(__dsub_rn(i22, __dmul_rn(r02, r02)), __dmul_rn(r12, r12));
+        ok = p22 > 0.0;
+        if (ok) {
+          const double r22 = __dsqrt_rn(p22);
+          R[0] = r00; R[1] = r01; R[2] = r02; R[4] = r11; R[5] = r12; R[8] = r22;
+          for (int q = 0; q < 9; ++q) ok = ok && isfinite(R[q]);
+        }
+      }
+    }
+  }
+  if (!ok)
+    for (int q = 0; q < 9; ++q) R[q] = 0.0;
+  for (int q = 0; q < 9; ++q) f.sqrt_info[q] = R[q];
+  f.status = r.status | (ok ? 0u : DPGICP_FLAG_FACTOR_INVALID);
+  out[k] = f;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * FP32-pipe probe: the roofline denominator of the distance loop, measured on the device in use.
  * 8 independent dependent-chains per thread of separately rounded FMUL + FADD (the instruction mix
  * the bit-exact distance loop is allowed to use; FMA = false) or of FFMA (FMA = true, for context).

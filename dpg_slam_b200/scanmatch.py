@@ -18,7 +18,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _abi
-from ._abi import Params, Result, RESULT_DTYPE
+from ._abi import FACTOR_DTYPE, Params, Result, RESULT_DTYPE
 
 
 class DpgIcpError(RuntimeError):
@@ -135,6 +135,7 @@ class ScanMatcher:
         if not (s.shape[0] == t.shape[0] == g.shape[0]):
             raise ValueError("src_idx, tgt_idx and guess must have the same length")
         out = np.zeros(s.shape[0], RESULT_DTYPE)
+        self._n_pairs = s.shape[0]
         self._check(self._lib.dpgicp_submit_pairs(self._h, s.ctypes.data, t.ctypes.data, g.ctypes.data, s.shape[0],
                                                   C.byref(params), out.ctypes.data))
         return out
@@ -155,6 +156,14 @@ class ScanMatcher:
         if out is None:
             out = np.zeros(n, RESULT_DTYPE)
         self._check(self._lib.dpgicp_fetch_results(self._h, out.ctypes.data, n))
+        return out
+
+    def fetch_factors(self, n: Optional[int] = None) -> np.ndarray:
+        """Records of the last run as pose-graph factors (``addObservationConstraint``, dpg_slam.cc:331-338):
+        from/to node, Pose2 and the upper-triangular square-root information of the covariance."""
+        n = self._n_pairs if n is None else n
+        out = np.zeros(n, FACTOR_DTYPE)
+        self._check(self._lib.dpgicp_fetch_factors(self._h, out.ctypes.data, n))
         return out
 
     def fetch_results_ptr(self, host_ptr: int, n: int):

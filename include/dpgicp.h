@@ -73,6 +73,7 @@ extern "C" {
 #define DPGICP_FLAG_CONVERGED         0x100u  /* == what icp.hasConverged() returns, dpg_slam.cc:445 */
 #define DPGICP_FLAG_COV_SINGULAR      0x200u  /* Hessian not invertible; cov fell back to the LIVE diagonal */
 #define DPGICP_FLAG_EMPTY_INPUT       0x400u  /* a cloud of the pair had no points                */
+#define DPGICP_FLAG_FACTOR_INVALID    0x800u  /* dpgicp_factor only: cov is not positive definite  */
 
 /* ---- parameter block (defaults = src/dpg_slam/parameters.h, see dpgicp_default_params) ---- */
 typedef struct dpgicp_params {
@@ -104,6 +105,18 @@ typedef struct dpgicp_result {
   double   mse;           /* mean squared correspondence distance of the last executed iteration   */
   double   cov[9];        /* 3x3, axes (x, y, theta), row-major (symmetric)  cov.h:564-566,573-575  */
 } dpgicp_result;
+
+/* ---- pose-graph factor (the hand-off of addObservationConstraint, dpg_slam.cc:331-338) -------- */
+/* BetweenFactor<Pose2>(from, to, Pose2(tx, ty, theta), noiseModel::Gaussian::Covariance(cov)): GTSAM
+ * turns the covariance into the upper-triangular square-root information R (R^T R = cov^-1); it is
+ * computed here on the device so the host does no per-factor linear algebra
+ * (noiseModel::Gaussian::SqrtInformation(R)).                                                     */
+typedef struct dpgicp_factor {          /* 96 bytes */
+  int32_t  from_node, to_node;          /* target scan (node_1), source scan (node_2)                 */
+  float    tx, ty, theta;               /* pose of to_node in from_node's frame                        */
+  uint32_t status;                      /* the record's status | DPGICP_FLAG_FACTOR_INVALID           */
+  double   sqrt_info[9];                /* R, row-major, upper triangular; zeros when invalid          */
+} dpgicp_factor;
 
 typedef struct dpgicp_ctx dpgicp_ctx;
 
@@ -151,6 +164,8 @@ int  dpgicp_set_pairs(dpgicp_ctx *ctx, const int32_t *src_idx, const int32_t *tg
                       const float *guess, int64_t n_pairs);            /* H2D of the pair list   */
 int  dpgicp_run(dpgicp_ctx *ctx, const dpgicp_params *params);         /* async on ctx stream    */
 int  dpgicp_fetch_results(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n_pairs); /* D2H + sync   */
+/* Records of the last dpgicp_run turned into pose-graph factors on the device (one per pair, pair order). */
+int  dpgicp_fetch_factors(dpgicp_ctx *ctx, dpgicp_factor *out, int64_t n_pairs);
 /* device address of the record array written by dpgicp_run (n_pairs * sizeof(dpgicp_result));
  * lets a multi-GPU host gather records device-to-device (NCCL) without a host bounce.          */
 int  dpgicp_results_device_ptr(dpgicp_ctx *ctx, void **out_ptr, int64_t *out_n_pairs);

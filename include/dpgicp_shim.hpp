@@ -133,6 +133,13 @@ class ScanMatcher {
           "dpgicp_submit_pairs");
     return out;
   }
+  /* the batch just run as pose-graph factors: BetweenFactor<Pose2>(from, to, Pose2(tx, ty, theta),
+   * noiseModel::Gaussian::SqrtInformation(R)) — addObservationConstraint, dpg_slam.cc:331-338 */
+  std::vector<dpgicp_factor> factors(size_t n) {
+    std::vector<dpgicp_factor> out(n);
+    check(dpgicp_fetch_factors(ctx_, out.data(), (int64_t)n), "dpgicp_fetch_factors");
+    return out;
+  }
 
  private:
   void check(int rc, const char *what) {

@@ -657,6 +657,45 @@ int orc_run_batch(const float *points, const int64_t *offsets, int n_scans,
   return used;
 }
 
+/* dpg_slam.cc:331-338: Pose2(tx, ty, theta) + Gaussian::Covariance(cov) -> sqrt information */
+void orc_factor(const dpgicp_result *r, int32_t src, int32_t tgt, dpgicp_factor *f) {
+  f->from_node = tgt; f->to_node = src;
+  f->tx = r->tx; f->ty = r->ty; f->theta = r->theta;
+  const double a = r->cov[0], b = r->cov[1], c = r->cov[2], d = r->cov[4], e = r->cov[5], g = r->cov[8];
+  const double c00 = (d * g) - (e * e);
+  const double c01 = (c * e) - (b * g);
+  const double c02 = (b * e) - (c * d);
+  const double det = ((a * c00) + (b * c01)) + (c * c02);
+  int ok = (det > 0.0) && isfinite(det);
+  double R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (ok) {
+    const double id = 1.0 / det;
+    const double i00 = c00 * id, i01 = c01 * id, i02 = c02 * id;
+    const double i11 = ((a * g) - (c * c)) * id;
+    const double i12 = ((b * c) - (a * e)) * id;
+    const double i22 = ((a * d) - (b * b)) * id;
+    ok = i00 > 0.0;
+    if (ok) {
+      const double r00 = sqrt(i00);
+      const double r01 = i01 / r00, r02 = i02 / r00;
+      const double p11 = i11 - (r01 * r01);
+      ok = p11 > 0.0;
+      if (ok) {
+        const double r11 = sqrt(p11);
+        const double r12 = (i12 - (r01 * r02)) / r11;
+        const double p22 = (i22 - (r02 * r02)) - (r12 * r12);
+        ok = p22 > 0.0;
+        if (ok) {
+          R[0] = r00; R[1] = r01; R[2] = r02; R[4] = r11; R[5] = r12; R[8] = sqrt(p22);
+          for (int q = 0; q < 9; ++q) ok = ok && isfinite(R[q]);
+        }
+      }
+    }
+  }
+  for (int q = 0; q < 9; ++q) f->sqrt_info[q] = ok ? R[q] : 0.0;
+  f->status = r->status | (ok ? 0u : DPGICP_FLAG_FACTOR_INVALID);
+}
+
 /* dpg_slam.cc:79-107 (reoptimize): for node i > 0: the successive pair (i-1 -> i), then every
  * j < i-1 whose float distance passes the same-pass / other-pass gate.  source = node i. */
 int64_t orc_enumerate_pairs(const float *node_xy, const int32_t *node_pass, int n_nodes,

@@ -87,6 +87,10 @@ int   orc_run_batch(const float *points, const int64_t *offsets, int n_scans,
                     int64_t n_pairs, const dpgicp_params *p, int fast, int threads,
                     dpgicp_result *out);
 
+/* addObservationConstraint hand-off (dpg_slam.cc:331-338): record -> factor with the upper-triangular
+ * square-root information R (R^T R = cov^-1), as noiseModel::Gaussian::Covariance derives it      */
+void  orc_factor(const dpgicp_result *rec, int32_t src, int32_t tgt, dpgicp_factor *out);
+
 /* callers' pair enumeration (dpg_slam.cc:79-107): returns count; writes up to capacity pairs    */
 int64_t orc_enumerate_pairs(const float *node_xy, const int32_t *node_pass, int n_nodes,
                             float same_pass_radius, float other_pass_radius,

@@ -14,7 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(_HERE))
-from dpg_slam_b200._abi import Params, Result, RESULT_DTYPE  # noqa: E402  (shared POD types only)
+from dpg_slam_b200._abi import FACTOR_DTYPE, Params, Result, RESULT_DTYPE  # noqa: E402  (shared POD types only)
 
 _lib = None
 
@@ -55,6 +55,8 @@ def lib() -> C.CDLL:
         L.orc_run_pair.argtypes = [vp, C.c_int, vp, C.c_int, vp, PP, C.c_int, C.POINTER(Result)]
         L.orc_run_batch.restype = C.c_int
         L.orc_run_batch.argtypes = [vp, vp, C.c_int, vp, vp, vp, i64, PP, C.c_int, C.c_int, vp]
+        L.orc_factor.restype = None
+        L.orc_factor.argtypes = [vp, i32, i32, vp]
         L.orc_enumerate_pairs.restype = i64
         L.orc_enumerate_pairs.argtypes = [vp, vp, C.c_int, f, f, vp, vp, i64]
         _lib = L
@@ -185,3 +187,12 @@ def enumerate_pairs(node_xy, node_pass, same_radius, other_radius):
     lib().orc_enumerate_pairs(xy.ctypes.data, ps.ctypes.data, xy.shape[0], same_radius, other_radius,
                               src.ctypes.data, tgt.ctypes.data, n)
     return src, tgt
+
+
+def factors(records, src_idx, tgt_idx):
+    """records (RESULT_DTYPE array) -> FACTOR_DTYPE array (orc_factor per pair)"""
+    rec = np.ascontiguousarray(records)
+    out = np.zeros(rec.shape[0], FACTOR_DTYPE)
+    for k in range(rec.shape[0]):
+        lib().orc_factor(rec[k:k + 1].ctypes.data, int(src_idx[k]), int(tgt_idx[k]), out[k:k + 1].ctypes.data)
+    return out

@@ -313,6 +313,53 @@ def test_enumerate_pairs_matches_oracle(gpu_matcher):
         assert np.array_equal(src, wsrc) and np.array_equal(tgt, wtgt), n
 
 
+def test_factor_handoff_matches_oracle(gpu_matcher):
+    """addObservationConstraint hand-off (dpg_slam.cc:331-338): from/to, Pose2, sqrt information R with
+    R^T R = cov^-1; bit-exact against the oracle applied to the same records."""
+    wl = synth.config_loop_closure(n_pairs=300, n_scans=100, seed=41)
+    wl.guess[7] = (70.0, 70.0, 0.0)                                   # a pair with no correspondences
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    for cov_mode in (COV_CENSI_CORR, COV_REFERENCE_LIVE):
+        p = Params.defaults(downsample_divisor=1, cov_mode=cov_mode)
+        rec = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+        got = gpu_matcher.fetch_factors()
+        want = O.factors(rec, wl.src_idx, wl.tgt_idx)
+        assert got.tobytes() == want.tobytes()
+        assert np.array_equal(got["from_node"], wl.tgt_idx) and np.array_equal(got["to_node"], wl.src_idx)
+        ok = (got["status"] & _abi.FLAG_FACTOR_INVALID) == 0
+        assert ok.all()
+        R = got["sqrt_info"].reshape(-1, 3, 3)
+        info = np.einsum("kji,kjl->kil", R, R)
+        cov = rec["cov"].reshape(-1, 3, 3)
+        eye = np.einsum("kij,kjl->kil", info, cov)
+        assert np.abs(eye - np.eye(3)).max() < 1e-6
+        assert np.all(np.tril(R, -1) == 0)
+    # a covariance that is not positive definite is flagged and zeroed, never passed on
+    assert gpu_matcher.fetch_factors(0).shape == (0,)
+
+
+def test_config5_multisession_gated_pairs(gpu_matcher):
+    """BASELINE config 5 shape at oracle size: sessions on a shared, partly changed world; candidate pairs from
+    the callers' distance gate (5 m same pass / 2 m across passes) enumerated on the device; guesses from the
+    drifted node estimates exactly as runIcp derives them."""
+    from dpg_slam_b200.scanmatch import relative_guess
+    wl = synth.config_multisession(n_sessions=3, scans_per_session=60, n_beams=541, seed=5, size=30.0, n_boxes=30)
+    src, tgt = gpu_matcher.enumerate_pairs(wl.poses_est[:, :2], wl.passes, 5.0, 2.0)
+    wsrc, wtgt = O.enumerate_pairs(wl.poses_est[:, :2], wl.passes, 5.0, 2.0)
+    assert np.array_equal(src, wsrc) and np.array_equal(tgt, wtgt) and len(src) > 180
+    guess = np.stack([relative_guess(wl.poses_est[t], wl.poses_est[s]) for s, t in zip(src, tgt)])
+    og = np.stack([O.relative_guess(wl.poses_est[t, :2], float(wl.poses_est[t, 2]), wl.poses_est[s, :2],
+                                    float(wl.poses_est[s, 2])) for s, t in zip(src, tgt)])
+    assert guess.tobytes() == og.tobytes()
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    pts, off = gpu_matcher.download_store()
+    for metric in (0, METRIC_POINT_TO_LINE):
+        p = Params.defaults(cov_mode=COV_CENSI_CORR, metric=metric)          # reference defaults: divisor 5
+        got = gpu_matcher.submit_pairs(src, tgt, guess, p)
+        ref, _ = O.run_batch(pts, off, src, tgt, guess, p, fast=1, threads=0)
+        assert_records_match(got, ref, f"multisession m{metric}")
+
+
 # ---- size-independent properties at full batch sizes ------------------------------------------------------------
 def test_full_size_batch_properties(gpu_matcher):
     """BASELINE config 2 at full size (5000 pairs, 1081 beams): the oracle checks a strided sample; the

@@ -265,3 +265,19 @@ def test_point_to_line_isolated_points_fall_back_to_point_rows():
     res = O.run_pair(src, tgt, [0, 0, 0], p)
     assert res.status & FLAG_CONVERGED and res.n_correspondences == 60
     assert abs(res.theta - th) < 1e-4
+
+
+def test_factor_sqrt_information():
+    from dpg_slam_b200._abi import FLAG_FACTOR_INVALID, RESULT_DTYPE
+    r = np.zeros(3, RESULT_DTYPE)
+    C = np.array([[4e-5, -5e-6, 3e-6], [-5e-6, 5e-5, -1e-6], [3e-6, -1e-6, 2e-6]])
+    r["cov"][0] = C.reshape(9)
+    r["cov"][1] = np.diag([0.5, 0.5, 0.3]).reshape(9)            # the reference's live covariance
+    r["cov"][2] = np.array([[1, 2, 0], [2, 1, 0], [0, 0, 1]], float).reshape(9)   # indefinite
+    r["tx"], r["theta"] = [1, 2, 3], [0.1, 0.2, 0.3]
+    f = O.factors(r, [1, 2, 3], [0, 1, 2])
+    R = f["sqrt_info"][0].reshape(3, 3)
+    assert np.allclose(R.T @ R, np.linalg.inv(C), rtol=1e-12) and np.all(np.tril(R, -1) == 0)
+    assert np.allclose(f["sqrt_info"][1].reshape(3, 3), np.diag([2 ** 0.5, 2 ** 0.5, (1 / 0.3) ** 0.5]))
+    assert f["status"][2] & FLAG_FACTOR_INVALID and not f["sqrt_info"][2].any()
+    assert list(f["from_node"]) == [0, 1, 2] and list(f["to_node"]) == [1, 2, 3] and f["tx"][1] == 2
