@@ -220,7 +220,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
       widths[n_stages++] = w;
     }
   }
-  CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, 24 * sizeof(unsigned long long), ctx->stream));
   int grid_prev = 0;
   if (n_stages > 1) {
     /* every stage can suspend at most one pair per CTA: size the state slots for stage 0's grid */
@@ -421,7 +421,7 @@ int dpgicp_create(int device, dpgicp_ctx **out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaMalloc((void **)&ctx->d_queue, 16 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc((void **)&ctx->d_queue, 24 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMalloc((void **)&ctx->d_bad, sizeof(int))) != cudaSuccess) {
     delete ctx;
     return fail(nullptr, DPGICP_E_CUDA, cudaGetErrorString(e));
@@ -602,6 +602,17 @@ int dpgicp_last_run_counters(dpgicp_ctx *ctx, uint64_t counters[8]) {
   counters[4] = ctx->launches;
   return DPGICP_OK;
 }
+
+#ifdef DPGICP_PHASE_TIMING
+/* development builds only: cycles thread 0 spent in each phase of the pass loop, summed over pairs */
+int dpgicp_debug_phase_counters(dpgicp_ctx *ctx, uint64_t out[8]) {
+  unsigned long long h[8];
+  CU_TRY(ctx, cudaMemcpyAsync(h, ctx->d_queue + 16, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 8; ++k) out[k] = h[k];
+  return DPGICP_OK;
+}
+#endif
 
 int dpgicp_submit_pairs(dpgicp_ctx *ctx, const int32_t *src, const int32_t *tgt, const float *guess, int64_t n,
                         const dpgicp_params *params, dpgicp_result *out) {

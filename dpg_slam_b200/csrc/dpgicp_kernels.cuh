@@ -548,7 +548,7 @@ __device__ __forceinline__ long long fxp(double v) { return __double2ll_rn(__dmu
 #define DPGICP_TARGET_WARPS 24
 #endif
 __host__ __device__ constexpr int min_ctas(int warps) {
-  return (DPGICP_TARGET_WARPS / warps) < 1 ? 1 : (DPGICP_TARGET_WARPS / warps) > 16 ? 16 : (DPGICP_TARGET_WARPS / warps);
+  return (DPGICP_TARGET_WARPS / warps) < 1 ? 1 : (DPGICP_TARGET_WARPS / warps) > 16 ? 16 : (DPGICP_TARGET_WARPS / warps);   /* 16, 17, 32 -> 1 */
 }
 
 template <int WARPS, bool PRUNED>
@@ -661,6 +661,13 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
     }
 
     int stop = 0;
+#ifdef DPGICP_PHASE_TIMING
+    long long ph[6] = {0, 0, 0, 0, 0, 0};
+#define PH_MARK(k) do { if (tid == 0) { const long long now__ = clock64(); ph[k] += now__ - ph_t; ph_t = now__; } } while (0)
+    long long ph_t = clock64();
+#else
+#define PH_MARK(k) do { } while (0)
+#endif
     for (;;) {
       long long m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, m6 = 0, m7 = 0, m8 = 0, m_d2 = 0;
       int m_k = 0;
@@ -726,6 +733,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           m_k += 1;
         }
       }
+      PH_MARK(0);                                     /* own tiles */
       /* exact integer reduction: warp shuffles, then one shared atomic per warp and value */
       m0 = warp_sum_i64(m0); m1 = warp_sum_i64(m1); m2 = warp_sum_i64(m2);
       m3 = warp_sum_i64(m3); m4 = warp_sum_i64(m4); m5 = warp_sum_i64(m5);
@@ -740,7 +748,9 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         atomicAdd(r + 8, (unsigned long long)m8); atomicAdd(r + 9, (unsigned long long)m_d2);
         atomicAdd(r + 10, (unsigned long long)(long long)m_k);
       }
+      PH_MARK(1);                                     /* warp reduction + shared atomics */
       __syncthreads();
+      PH_MARK(2);                                     /* wait for the other warps */
 
       if (tid == 0) {
         /* has this stage's queue run dry?  (read early, the L2 round trip overlaps the solve) */
@@ -793,6 +803,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
 #pragma unroll
         for (int k = 0; k < 11; ++k) L.red[k] = 0;
       }
+      PH_MARK(3);                                     /* solve + convergence */
       __syncthreads();
       stop = L.ctl[2];
       c_corr += (tid == 0) ? (unsigned long long)L.ctl[3] : 0ull;
@@ -808,9 +819,15 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         }
       }
       if (tid == 0) ++c_iters;
+      PH_MARK(4);                                     /* transform + boxes (own tiles) */
       __syncthreads();
+      PH_MARK(5);                                     /* wait */
       if (stop) break;
     }
+#ifdef DPGICP_PHASE_TIMING
+    if (tid == 0)
+      for (int k = 0; k < 6; ++k) atomicAdd(P.counters + 8 + k, (unsigned long long)ph[k]);   /* d_queue[16..21] */
+#endif
 
     if (stop == 3) {
       /* ---- suspend: current source cloud + seeds + scalars -> state slot, pair -> next queue --- */
