@@ -173,7 +173,7 @@ def run_reference(args):
     wl = make_workload(PAIRS_PER_GPU)
     p = bench_params()
     pts, off = oracle_clouds(wl)
-    idx, used = choose_cpu_sample(wl, pts, off, p, target_s=8.0)
+    idx, used = choose_cpu_sample(wl, pts, off, p, target_s=float(os.environ.get("DPGICP_BENCH_CPU_TARGET_S", "8.0")))
     for _ in range(max(args.warmup, 0)):
         cpu_sample_run(wl, pts, off, p, idx[:max(8, len(idx) // 8)])
     t_total = 0.0
