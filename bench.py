@@ -290,9 +290,19 @@ def run_product(args):
         out_pin = torch.empty(len(idx) * sharded.RECORD_BYTES, dtype=torch.uint8).pin_memory()
         src_l, tgt_l, guess_l = wl.src_idx[idx], wl.tgt_idx[idx], wl.guess[idx]
 
+        used = None
+        if world > 1:      # a rank needs only the scans its shard touches: read in place from page-locked memory
+            used = shard.plan_subset(wl.src_idx, wl.tgt_idx, wl.n_scans)
+            src_e, tgt_e = shard._remap[src_l], shard._remap[tgt_l]
+        else:
+            src_e, tgt_e = src_l, tgt_l
+
         def step_e2e():
-            sm.upload_ranges_ptr(ranges_pin.data_ptr(), wl.n_scans, N_BEAMS, wl.scanner)     # H2D + scan->cloud
-            sm.set_pairs(src_l, tgt_l, guess_l)                                              # H2D pair list
+            if used is None:
+                sm.upload_ranges_ptr(ranges_pin.data_ptr(), wl.n_scans, N_BEAMS, wl.scanner) # H2D + scan->cloud
+            else:
+                sm.upload_ranges_subset(ranges_pin.data_ptr(), used, wl.scanner, n_scans_total=wl.n_scans, n_beams=N_BEAMS)
+            sm.set_pairs(src_e, tgt_e, guess_l)                                              # H2D pair list
             sm.run(p)
             if world > 1:
                 shard.gather_device()
@@ -311,8 +321,9 @@ def run_product(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_value = n_global * e2e_steps / float(t.item())
-        h2d = int(wl.ranges.nbytes + 24 * len(idx))
-        d2h = int(sharded.RECORD_BYTES * len(idx) + 4 * wl.n_scans + 4)
+        n_up = wl.n_scans if used is None else len(used)
+        h2d = int(4 * N_BEAMS * n_up + 24 * len(idx) + (0 if used is None else 4 * n_up))
+        d2h = int(sharded.RECORD_BYTES * len(idx) + 4 * n_up + 4)
         e2e_rec = np.frombuffer(out_pin.numpy().tobytes(), dtype=rec_local.dtype)
         assert e2e_rec.tobytes() == rec_local.tobytes(), "e2e records differ from the resident-arm records"
 

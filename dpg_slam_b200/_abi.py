@@ -99,7 +99,7 @@ assert C.sizeof(Params) == 72
 EXPORTS = [
     "dpgicp_abi_version", "dpgicp_default_params", "dpgicp_create", "dpgicp_destroy",
     "dpgicp_last_error", "dpgicp_set_stream", "dpgicp_synchronize", "dpgicp_upload_scans",
-    "dpgicp_upload_ranges", "dpgicp_scan_count", "dpgicp_download_scan", "dpgicp_submit_pairs",
+    "dpgicp_upload_ranges", "dpgicp_upload_ranges_subset", "dpgicp_scan_count", "dpgicp_download_scan", "dpgicp_submit_pairs",
     "dpgicp_set_pairs", "dpgicp_run", "dpgicp_fetch_results", "dpgicp_fetch_factors", "dpgicp_results_device_ptr",
     "dpgicp_last_run_counters", "dpgicp_single_pair", "dpgicp_cov", "dpgicp_correspondences",
     "dpgicp_enumerate_pairs", "dpgicp_relative_guess", "dpgicp_fp32_probe",
@@ -136,6 +136,7 @@ def load_library() -> C.CDLL:
         "dpgicp_synchronize": (C.c_int, [vp]),
         "dpgicp_upload_scans": (C.c_int, [vp, vp, sz, vp, i32]),
         "dpgicp_upload_ranges": (C.c_int, [vp, vp, i32, i32] + [C.c_float] * 6),
+        "dpgicp_upload_ranges_subset": (C.c_int, [vp, vp, i32, i32, vp, i32] + [C.c_float] * 6),
         "dpgicp_scan_count": (C.c_int, [vp]),
         "dpgicp_download_scan": (C.c_int, [vp, i32, vp, C.POINTER(i32)]),
         "dpgicp_submit_pairs": (C.c_int, [vp, vp, vp, vp, i64, PP, vp]),

@@ -58,6 +58,8 @@ struct dpgicp_ctx {
   int max_stages = 4;
   std::vector<int> chain;                    /* DPGICP_CHAIN: target warps per stage (development knob) */
   int *d_bad = nullptr;
+  void *h_stage = nullptr;                   /* pinned staging for subset uploads from pageable memory */
+  size_t h_stage_cap = 0;
   int force_warps = 0;
   int force_ctas_per_sm = 0;
   uint64_t launches = 0;
@@ -453,6 +455,7 @@ void dpgicp_destroy(dpgicp_ctx *ctx) {
   for (int k = 0; k < 2; ++k) { release(ctx->state[k]); release(ctx->susp[k]); }
   if (ctx->d_queue) cudaFree(ctx->d_queue);
   if (ctx->d_bad) cudaFree(ctx->d_bad);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -512,12 +515,72 @@ int dpgicp_upload_ranges(dpgicp_ctx *ctx, const float *ranges, int32_t n_scans, 
   const float lc = cosf(ltheta), ls = sinf(ltheta);       /* Eigen::Rotation2Df(ltheta), host libm */
   const int threads = 128, warps_per_block = threads / 32;
   const int blocks = (n_scans + warps_per_block - 1) / warps_per_block;
-  ranges_to_rows_kernel<<<blocks, threads, 0, ctx->stream>>>((const float *)ctx->stage.p, n_scans, n_beams, angle_min,
+  ranges_to_rows_kernel<<<blocks, threads, 0, ctx->stream>>>((const float *)ctx->stage.p, nullptr, n_scans, n_beams, angle_min,
                                                             angle_inc, range_max, lx, ly, lc, ls, pitch,
                                                             (float2 *)st.rows.p, (int32_t *)st.count.p, ctx->d_bad);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   return finish_store(ctx, st, n_scans);
+}
+
+int dpgicp_upload_ranges_subset(dpgicp_ctx *ctx, const float *ranges, int32_t n_scans_total, int32_t n_beams,
+                                const int32_t *scan_ids, int32_t n_ids, float angle_min, float angle_max, float range_max,
+                                float lx, float ly, float ltheta) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_scans_total < 0 || n_ids < 0 || n_beams < 2 || (n_ids > 0 && (!ranges || !scan_ids)))
+    return fail(ctx, DPGICP_E_INVALID, "bad range-scan arguments");
+  if (n_beams > DPGICP_MAX_POINTS) return fail(ctx, DPGICP_E_TOOBIG, "n_beams exceeds DPGICP_MAX_POINTS");
+  for (int32_t k = 0; k < n_ids; ++k)
+    if (scan_ids[k] < 0 || scan_ids[k] >= n_scans_total)
+      return fail(ctx, DPGICP_E_INVALID, "scan id out of range at position " + std::to_string(k));
+  Store &st = ctx->store;
+  ctx->batch.n_pairs = 0;
+  const int pitch = (n_beams + 1) & ~1;
+  int rc;
+  if ((rc = reserve(ctx, st.rows, sizeof(float2) * (size_t)pitch * (size_t)std::max(n_ids, 1)))) return rc;
+  if ((rc = reserve(ctx, st.count, sizeof(int32_t) * (size_t)std::max(n_ids, 1)))) return rc;
+  st.pitch = pitch;
+  st.n_scans = 0;
+  if (n_ids == 0) { st.max_count = 0; st.h_count.clear(); return DPGICP_OK; }
+  CU_TRY(ctx, cudaMemsetAsync(ctx->d_bad, 0, sizeof(int), ctx->stream));
+  /* page-locked input: the kernel reads the selected rows straight from host memory, so only they cross the
+   * bus and nothing is staged; pageable input: gather the rows through a pinned buffer and copy them */
+  cudaPointerAttributes attr;
+  const bool mapped = cudaPointerGetAttributes(&attr, ranges) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                      attr.devicePointer != nullptr;
+  cudaGetLastError();
+  const float *d_in = nullptr;
+  const int32_t *d_ids = nullptr;
+  if (mapped) {
+    if ((rc = reserve(ctx, ctx->offsets, sizeof(int32_t) * (size_t)n_ids))) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->offsets.p, scan_ids, sizeof(int32_t) * (size_t)n_ids, cudaMemcpyHostToDevice, ctx->stream));
+    d_in = (const float *)attr.devicePointer;
+    d_ids = (const int32_t *)ctx->offsets.p;
+  } else {
+    const size_t bytes = sizeof(float) * (size_t)n_ids * (size_t)n_beams;
+    if (bytes > ctx->h_stage_cap) {
+      if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+      ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+      CU_TRY(ctx, cudaMallocHost(&ctx->h_stage, bytes));
+      ctx->h_stage_cap = bytes;
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));       /* the buffer may still feed a previous copy */
+    for (int32_t k = 0; k < n_ids; ++k)
+      std::memcpy((float *)ctx->h_stage + (size_t)k * n_beams, ranges + (size_t)scan_ids[k] * n_beams, sizeof(float) * (size_t)n_beams);
+    if ((rc = reserve(ctx, ctx->stage, bytes + 16))) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->stage.p, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_in = (const float *)ctx->stage.p;
+  }
+  const float angle_inc = (float)(((double)(float)(angle_max - angle_min)) / ((double)n_beams - 1.0));
+  const float lc = cosf(ltheta), ls = sinf(ltheta);
+  const int threads = 128, warps_per_block = threads / 32;
+  const int blocks = (n_ids + warps_per_block - 1) / warps_per_block;
+  ranges_to_rows_kernel<<<blocks, threads, 0, ctx->stream>>>(d_in, d_ids, n_ids, n_beams, angle_min, angle_inc, range_max, lx, ly,
+                                                            lc, ls, pitch, (float2 *)st.rows.p, (int32_t *)st.count.p, ctx->d_bad);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  return finish_store(ctx, st, n_ids);
 }
 
 int dpgicp_scan_count(const dpgicp_ctx *ctx) { return ctx ? ctx->store.n_scans : DPGICP_E_INVALID; }

@@ -1041,12 +1041,14 @@ __global__ void pack_rows_kernel(const unsigned char *__restrict__ pts, size_t s
 /* raw ranges -> base_link points, MAX_RANGE dropped, beam order kept (createNode
  * dpg_slam.cc:497-506, dpg_measurement.h:41-46,102-104, dpg_node.cc:13-22).  One warp per scan,
  * ballot-prefix compaction.  Trig in binary64 rounded to binary32, like the oracle. */
-__global__ void ranges_to_rows_kernel(const float *__restrict__ ranges, int n_scans, int n_beams, float angle_min,
-                                      float angle_inc, float range_max, float lx, float ly, float lc, float ls,
-                                      int pitch, float2 *rows, int32_t *count, int *bad) {
+__global__ void ranges_to_rows_kernel(const float *__restrict__ ranges, const int32_t *__restrict__ scan_ids, int n_scans,
+                                      int n_beams, float angle_min, float angle_inc, float range_max, float lx, float ly,
+                                      float lc, float ls, int pitch, float2 *rows, int32_t *count, int *bad) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n_scans) return;
-  const float *r = ranges + (size_t)warp * n_beams;
+  /* store row `warp` is scan scan_ids[warp] of the input (identity when null); `ranges` may be pinned host
+   * memory, read directly over PCIe in coalesced 128-byte requests */
+  const float *r = ranges + (size_t)(scan_ids ? scan_ids[warp] : warp) * n_beams;
   float2 *row = rows + (size_t)warp * pitch;
   int n = 0;
   for (int base = 0; base < n_beams; base += 32) {

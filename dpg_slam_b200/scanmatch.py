@@ -109,6 +109,21 @@ class ScanMatcher:
                                                    scanner.angle_min, scanner.angle_max, scanner.range_max,
                                                    scanner.laser_x, scanner.laser_y, scanner.laser_theta))
 
+    def upload_ranges_subset(self, ranges, scan_ids, scanner, n_scans_total: Optional[int] = None,
+                             n_beams: Optional[int] = None):
+        """Store row k = scan ``scan_ids[k]`` of ``ranges`` (an (n_scans, n_beams) float32 array, or a raw host
+        pointer with ``n_scans_total``/``n_beams`` given).  Page-locked input is read in place by the kernel."""
+        ids = np.ascontiguousarray(scan_ids, np.int32)
+        if isinstance(ranges, int):
+            ptr, total, beams = ranges, int(n_scans_total), int(n_beams)
+        else:
+            r = np.ascontiguousarray(ranges, np.float32)
+            self._keep = r
+            ptr, total, beams = r.ctypes.data, r.shape[0], r.shape[1]
+        self._check(self._lib.dpgicp_upload_ranges_subset(self._h, C.c_void_p(ptr), total, beams, ids.ctypes.data, ids.shape[0],
+                                                          scanner.angle_min, scanner.angle_max, scanner.range_max,
+                                                          scanner.laser_x, scanner.laser_y, scanner.laser_theta))
+
     @property
     def scan_count(self) -> int:
         return int(self._lib.dpgicp_scan_count(self._h))

@@ -97,6 +97,29 @@ class ShardedScanMatcher:
         self.sm, self.rank, self.world, self.group, self.device = matcher, rank, world, group, device
         self.n_pairs = 0
         self._send = self._recv = None
+        self._remap = None
+
+    def plan_subset(self, src_idx, tgt_idx, n_scans_total: int) -> np.ndarray:
+        """The distinct scans this rank's pairs touch (ascending) — the rows of a per-rank store — and the
+        remapping of global scan ids to those rows, remembered for :meth:`set_pairs`."""
+        idx = shard_indices(int(len(src_idx)), self.rank, self.world)
+        used = np.unique(np.concatenate([np.asarray(src_idx)[idx], np.asarray(tgt_idx)[idx]])).astype(np.int32)
+        remap = np.full(int(n_scans_total), -1, np.int32)
+        remap[used] = np.arange(used.shape[0], dtype=np.int32)
+        self._remap = remap
+        return used
+
+    def upload_ranges_for_shard(self, ranges, scanner, src_idx, tgt_idx, n_scans_total=None, n_beams=None):
+        """Instead of replicating the whole scan store, upload only the scans this rank's pairs touch.  ``ranges``
+        is the full host array (or a raw pointer to page-locked memory, read in place by the kernel)."""
+        total = int(n_scans_total) if n_scans_total is not None else int(ranges.shape[0])
+        used = self.plan_subset(src_idx, tgt_idx, total)
+        self.sm.upload_ranges_subset(ranges, used, scanner, n_scans_total=n_scans_total, n_beams=n_beams)
+        return used
+
+    def use_full_store(self):
+        """Forget a subset plan: the store holds every scan again (global scan ids)."""
+        self._remap = None
 
     def set_pairs(self, src_idx, tgt_idx, guess):
         """Takes the GLOBAL pair list; keeps this rank's shard resident on its GPU."""
@@ -104,10 +127,14 @@ class ShardedScanMatcher:
         self.n_pairs = int(len(src_idx))
         idx = shard_indices(self.n_pairs, self.rank, self.world)
         g = np.ascontiguousarray(guess, np.float32).reshape(-1, 3)
-        self.sm.set_pairs(np.asarray(src_idx)[idx], np.asarray(tgt_idx)[idx], g[idx])
+        s_loc, t_loc = np.asarray(src_idx)[idx], np.asarray(tgt_idx)[idx]
+        if getattr(self, "_remap", None) is not None:       # the store holds only this shard's scans
+            s_loc, t_loc = self._remap[s_loc], self._remap[t_loc]
+        self.sm.set_pairs(s_loc, t_loc, g[idx])
         m = padded_len(self.n_pairs, self.world)
-        self._send = torch.zeros(m * RECORD_BYTES, dtype=torch.uint8, device=self.device)
-        self._recv = torch.empty(self.world * m * RECORD_BYTES, dtype=torch.uint8, device=self.device)
+        if self._send is None or self._send.numel() != m * RECORD_BYTES:
+            self._send = torch.zeros(m * RECORD_BYTES, dtype=torch.uint8, device=self.device)
+            self._recv = torch.empty(self.world * m * RECORD_BYTES, dtype=torch.uint8, device=self.device)
 
     def run(self, params):
         self.sm.run(params)

@@ -147,6 +147,14 @@ int  dpgicp_upload_ranges(dpgicp_ctx *ctx, const float *ranges, int32_t n_scans,
                           float angle_min, float angle_max, float range_max,
                           float laser_x, float laser_y, float laser_theta);
 
+/* The same conversion for a SUBSET of the scans of a host array: store row k = scan scan_ids[k].  A GPU that
+ * holds a shard of the pairs needs only the scans its pairs touch.  When `ranges` is page-locked host memory the
+ * kernel reads the selected rows directly over PCIe (no staging, only those rows cross the bus); pageable
+ * memory is gathered through an internal pinned buffer.                                                      */
+int  dpgicp_upload_ranges_subset(dpgicp_ctx *ctx, const float *ranges, int32_t n_scans_total, int32_t n_beams,
+                                 const int32_t *scan_ids, int32_t n_ids, float angle_min, float angle_max,
+                                 float range_max, float laser_x, float laser_y, float laser_theta);
+
 int  dpgicp_scan_count(const dpgicp_ctx *ctx);
 /* copy scan k of the store back to the host (packed float2); *n_points in = capacity, out = count */
 int  dpgicp_download_scan(dpgicp_ctx *ctx, int32_t scan, float *xy, int32_t *n_points);

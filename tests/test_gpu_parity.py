@@ -60,6 +60,35 @@ def test_upload_ranges_matches_oracle_cloud_bit_exact(gpu_matcher):
     assert gpu_matcher.download_scan(5).shape == (0, 2)
 
 
+def test_upload_ranges_subset_pinned_and_pageable(gpu_matcher):
+    """A per-rank store holds only the scans its pairs touch; page-locked input is read in place by the kernel."""
+    import torch
+    wl = synth.config_corridor(n_pairs=60, n_beams=721, seed=14)
+    ids = np.array([5, 0, 17, 17, 60, 3], np.int32)
+    want = [O.ranges_to_cloud(wl.ranges[k], wl.scanner) for k in ids]
+    pinned = torch.from_numpy(wl.ranges).pin_memory()
+    for src in (wl.ranges, pinned.data_ptr()):
+        gpu_matcher.upload_ranges_subset(src, ids, wl.scanner, n_scans_total=wl.n_scans, n_beams=721)
+        assert gpu_matcher.scan_count == len(ids)
+        for row, w in enumerate(want):
+            got = gpu_matcher.download_scan(row)
+            assert got.shape == w.shape and got.tobytes() == w.tobytes()
+    with pytest.raises(DpgIcpError) as e:
+        gpu_matcher.upload_ranges_subset(wl.ranges, np.array([61], np.int32), wl.scanner)
+    assert e.value.code == -1
+    # aligning through the subset store with remapped indices == aligning through the full store
+    from dpg_slam_b200 import sharded
+    p = Params.defaults(cov_mode=COV_CENSI_CORR)
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    full = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+    sh = sharded.ShardedScanMatcher(gpu_matcher, 1, 3)
+    sh.upload_ranges_for_shard(pinned.data_ptr(), wl.scanner, wl.src_idx, wl.tgt_idx, n_scans_total=wl.n_scans, n_beams=721)
+    sh.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
+    sh.run(p)
+    part = gpu_matcher.fetch_results(sharded.shard_len(60, 1, 3))
+    assert part.tobytes() == full[sharded.shard_indices(60, 1, 3)].tobytes()
+
+
 def test_upload_scans_packed_and_pointxyz_stride_agree(gpu_matcher):
     wl = synth.config_corridor(n_pairs=3, n_beams=361, seed=4)
     pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
