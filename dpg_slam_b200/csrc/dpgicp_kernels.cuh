@@ -630,7 +630,6 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       }
       store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
     }
-    if (tid < 16) L.red[tid] = 0;
     __syncthreads();
 
     /* ---- parity hook: a single correspondence pass ------------------------------------------ */
@@ -740,18 +739,26 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       m6 = warp_sum_i64(m6); m7 = warp_sum_i64(m7); m8 = warp_sum_i64(m8); m_d2 = warp_sum_i64(m_d2);
       m_k = __reduce_add_sync(0xffffffffu, m_k);
       if (lane == 0) {
-        unsigned long long *r = reinterpret_cast<unsigned long long *>(L.red);
-        atomicAdd(r + 0, (unsigned long long)m0); atomicAdd(r + 1, (unsigned long long)m1);
-        atomicAdd(r + 2, (unsigned long long)m2); atomicAdd(r + 3, (unsigned long long)m3);
-        atomicAdd(r + 4, (unsigned long long)m4); atomicAdd(r + 5, (unsigned long long)m5);
-        atomicAdd(r + 6, (unsigned long long)m6); atomicAdd(r + 7, (unsigned long long)m7);
-        atomicAdd(r + 8, (unsigned long long)m8); atomicAdd(r + 9, (unsigned long long)m_d2);
-        atomicAdd(r + 10, (unsigned long long)(long long)m_k);
+        /* per-warp partials in shared memory (plain stores; a 64-bit shared atomicAdd is a CAS spin loop);
+         * the slots alias L.dpart, which is only used by the covariance after the pass loop */
+        long long *w = reinterpret_cast<long long *>(L.dpart) + warp * 12;
+        w[0] = m0; w[1] = m1; w[2] = m2; w[3] = m3; w[4] = m4; w[5] = m5; w[6] = m6; w[7] = m7; w[8] = m8;
+        w[9] = m_d2; w[10] = (long long)m_k;
       }
       PH_MARK(1);                                     /* warp reduction + shared atomics */
       __syncthreads();
       PH_MARK(2);                                     /* wait for the other warps */
 
+      if (warp == 0) {
+        /* exact integer totals: lane k adds value k over the warps (any order gives the same bits) */
+        if (lane < 11) {
+          const long long *w = reinterpret_cast<const long long *>(L.dpart) + lane;
+          long long tot = 0;
+          for (int q = 0; q < nw; ++q) tot += w[q * 12];
+          L.red[lane] = tot;
+        }
+        __syncwarp();
+      }
       if (tid == 0) {
         /* has this stage's queue run dry?  (read early, the L2 round trip overlaps the solve) */
         unsigned long long qhead = 0;
@@ -800,8 +807,6 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         }
         L.ctl[2] = st;
         L.ctl[3] = K;
-#pragma unroll
-        for (int k = 0; k < 11; ++k) L.red[k] = 0;
       }
       PH_MARK(3);                                     /* solve + convergence */
       __syncthreads();
