@@ -82,7 +82,7 @@ def workload_config(n_gpus: int, extra=None):
            "fov_deg": 270, "downsample_divisor": 1, "metric_kind": "point_to_line" if w["metric"] else "point_to_point",
            "reciprocal": True,
            "cov_mode": "CENSI_CORR(cap 200)", "max_iterations": 500, "max_correspondence_distance_m": 0.6,
-           "search": "exact pruned (bounding-box groups)", "sharding": f"round-robin over {n_gpus} GPU(s), scan store replicated",
+           "search": "exact pruned (bounding-box groups)", "sharding": f"round-robin over {n_gpus} GPU(s), scan store replicated, records gathered by peer stores from the kernel epilogue",
            "l2": "flushed between timed steps (512 MiB memset outside the event pair)", "seed": w["seed"]}
     if extra:
         cfg.update(extra)
@@ -242,9 +242,15 @@ def run_product(args):
         sm.upload_ranges(wl.ranges, wl.scanner)
         shard.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
 
+        # N > 1: the gather of the records is fused into the kernel epilogue (peer stores into every rank's
+        # whole-batch buffer over NVLink); DPGICP_BENCH_GATHER=nccl uses an all-gather collective after the kernel
+        fused = world > 1 and os.environ.get("DPGICP_BENCH_GATHER", "fused") != "nccl"
+        if fused:
+            shard.attach_fused_gather(n_global)
+
         def step_resident():
             shard.run(p)
-            if world > 1:
+            if world > 1 and not fused:
                 shard.gather_device()
 
         sampler = ClockSampler(local)          # started before the warm-up so that nvidia-smi is already sampling when
@@ -304,7 +310,7 @@ def run_product(args):
                 sm.upload_ranges_subset(ranges_pin.data_ptr(), used, wl.scanner, n_scans_total=wl.n_scans, n_beams=N_BEAMS)
             sm.set_pairs(src_e, tgt_e, guess_l)                                              # H2D pair list
             sm.run(p)
-            if world > 1:
+            if world > 1 and not fused:
                 shard.gather_device()
             sm.fetch_results_ptr(out_pin.data_ptr(), len(idx))                               # D2H records (syncs)
 
@@ -327,6 +333,10 @@ def run_product(args):
         e2e_rec = np.frombuffer(out_pin.numpy().tobytes(), dtype=rec_local.dtype)
         assert e2e_rec.tobytes() == rec_local.tobytes(), "e2e records differ from the resident-arm records"
 
+        if fused:
+            allrec = shard.fused_records()                                                   # whole batch, global order
+            assert allrec[idx].tobytes() == rec_local.tobytes(), "fused gather does not hold this rank's records"
+            shard.detach_fused_gather()
         probe = sm.fp32_probe() if rank == 0 else None
 
     if rank != 0:

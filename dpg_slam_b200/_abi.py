@@ -23,6 +23,8 @@ STOP_NONE, STOP_ITERATIONS, STOP_TRANSFORM, STOP_ABS_MSE, STOP_NO_CORRESPONDENCE
 FLAG_CONVERGED, FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT, FLAG_FACTOR_INVALID = 0x100, 0x200, 0x400, 0x800
 MAX_ABS_COORD = 1000.0
 MAX_POINTS = 8192
+IPC_HANDLE_BYTES = 64
+MAX_GATHER_RANKS = 16
 
 ERRORS = {0: "OK", -1: "E_INVALID", -2: "E_NODEVICE", -3: "E_CUDA", -4: "E_NOMEM", -5: "E_RANGE",
           -6: "E_STATE", -7: "E_TOOBIG"}
@@ -101,7 +103,8 @@ EXPORTS = [
     "dpgicp_last_error", "dpgicp_set_stream", "dpgicp_synchronize", "dpgicp_upload_scans",
     "dpgicp_upload_ranges", "dpgicp_upload_ranges_subset", "dpgicp_scan_count", "dpgicp_download_scan", "dpgicp_submit_pairs",
     "dpgicp_set_pairs", "dpgicp_run", "dpgicp_fetch_results", "dpgicp_fetch_factors", "dpgicp_results_device_ptr",
-    "dpgicp_last_run_counters", "dpgicp_single_pair", "dpgicp_cov", "dpgicp_correspondences",
+    "dpgicp_gather_export", "dpgicp_gather_attach", "dpgicp_gather_detach", "dpgicp_gather_fetch",
+    "dpgicp_gather_device_ptr", "dpgicp_last_run_counters", "dpgicp_single_pair", "dpgicp_cov", "dpgicp_correspondences",
     "dpgicp_enumerate_pairs", "dpgicp_relative_guess", "dpgicp_fp32_probe",
 ]
 
@@ -145,6 +148,11 @@ def load_library() -> C.CDLL:
         "dpgicp_fetch_results": (C.c_int, [vp, vp, i64]),
         "dpgicp_fetch_factors": (C.c_int, [vp, vp, i64]),
         "dpgicp_results_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "dpgicp_gather_export": (C.c_int, [vp, i64, vp]),
+        "dpgicp_gather_attach": (C.c_int, [vp, vp, i32, i32]),
+        "dpgicp_gather_detach": (C.c_int, [vp]),
+        "dpgicp_gather_fetch": (C.c_int, [vp, vp, i64]),
+        "dpgicp_gather_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "dpgicp_last_run_counters": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
         "dpgicp_single_pair": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, PR]),
         "dpgicp_cov": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, vp, C.POINTER(C.c_uint32)]),

@@ -55,6 +55,10 @@ struct dpgicp_ctx {
   DevBuf stage, offsets, misc, corr;
   DevBuf state[2], susp[2];                  /* suspended-pair state slots + pair lists, ping-pong between stages */
   unsigned long long *d_queue = nullptr;     /* [0..2] stage queue heads, [4],[5] suspended counts, [8..15] counters */
+  DevBuf gather;                             /* this rank's copy of the whole batch's records (fused gather)  */
+  int64_t gather_n = 0;
+  int gather_world = 0, gather_rank = 0;
+  void *gather_peer[DPGICP_MAX_GATHER_RANKS] = {nullptr};
   int max_stages = 4;
   std::vector<int> chain;                    /* DPGICP_CHAIN: target warps per stage (development knob) */
   int *d_bad = nullptr;
@@ -198,6 +202,13 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   kp.corr_out = corr_out;
   kp.corr_d2_out = corr_d2;
   kp.slot_bytes = (long long)kStateHeader + 12ll * n_cap;
+  if (ctx->gather_world > 1 && corr_out == nullptr && &b == &ctx->batch) {
+    if ((b.n_pairs - 1) * (int64_t)ctx->gather_world + ctx->gather_rank >= ctx->gather_n)
+      return fail(ctx, DPGICP_E_STATE, "the attached gather buffers are too small for this shard");
+    kp.gather_world = ctx->gather_world;
+    kp.gather_rank = ctx->gather_rank;
+    for (int g = 0; g < ctx->gather_world; ++g) kp.gather_peer[g] = (dpgicp_result *)ctx->gather_peer[g];
+  }
   const size_t smem = smem_bytes(n_cap);
   const bool pruned = p->search == DPGICP_SEARCH_PRUNED;
 
@@ -349,6 +360,16 @@ int set_pairs_into(dpgicp_ctx *ctx, const Store &st, Batch &b, const int32_t *sr
   return DPGICP_OK;
 }
 
+/* close the peer mappings of the fused gather */
+int gather_close(dpgicp_ctx *ctx) {
+  for (int g = 0; g < ctx->gather_world; ++g) {
+    if (g != ctx->gather_rank && ctx->gather_peer[g]) cudaIpcCloseMemHandle(ctx->gather_peer[g]);
+    ctx->gather_peer[g] = nullptr;
+  }
+  ctx->gather_world = 0;
+  return DPGICP_OK;
+}
+
 /* host repack of an arbitrary-stride cloud into packed float2 */
 void pack_host(const void *pts, int n, size_t stride, std::vector<float> &out) {
   out.resize((size_t)std::max(n, 0) * 2);
@@ -451,6 +472,8 @@ void dpgicp_destroy(dpgicp_ctx *ctx) {
     release(b->tasks); release(b->results);
     if (b->h_tasks) cudaFreeHost(b->h_tasks);
   }
+  gather_close(ctx);
+  release(ctx->gather);
   release(ctx->stage); release(ctx->offsets); release(ctx->misc); release(ctx->corr);
   for (int k = 0; k < 2; ++k) { release(ctx->state[k]); release(ctx->susp[k]); }
   if (ctx->d_queue) cudaFree(ctx->d_queue);
@@ -645,6 +668,72 @@ int dpgicp_fetch_factors(dpgicp_ctx *ctx, dpgicp_factor *out, int64_t n) {
   CU_TRY(ctx, cudaGetLastError());
   CU_TRY(ctx, cudaMemcpyAsync(out, ctx->stage.p, sizeof(dpgicp_factor) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
+}
+
+int dpgicp_gather_export(dpgicp_ctx *ctx, int64_t n_global, unsigned char handle_out[DPGICP_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle_out || n_global < 0) return DPGICP_E_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == DPGICP_IPC_HANDLE_BYTES, "IPC handle size");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  gather_close(ctx);
+  /* a dedicated cudaMalloc allocation (IPC handles cover whole allocations) */
+  release(ctx->gather);
+  int rc;
+  if ((rc = reserve(ctx, ctx->gather, sizeof(dpgicp_result) * (size_t)std::max<int64_t>(n_global, 1)))) return rc;
+  CU_TRY(ctx, cudaMemsetAsync(ctx->gather.p, 0, ctx->gather.cap, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->gather_n = n_global;
+  cudaIpcMemHandle_t h;
+  CU_TRY(ctx, cudaIpcGetMemHandle(&h, ctx->gather.p));
+  std::memcpy(handle_out, &h, sizeof(h));
+  return DPGICP_OK;
+}
+
+int dpgicp_gather_attach(dpgicp_ctx *ctx, const unsigned char *handles, int32_t world, int32_t rank) {
+  if (!ctx || !handles || world < 1 || world > DPGICP_MAX_GATHER_RANKS || rank < 0 || rank >= world) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->gather.p) return fail(ctx, DPGICP_E_STATE, "dpgicp_gather_export must be called first");
+  gather_close(ctx);
+  for (int g = 0; g < world; ++g) {
+    if (g == rank) { ctx->gather_peer[g] = ctx->gather.p; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)g * DPGICP_IPC_HANDLE_BYTES, sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      ctx->gather_world = g; ctx->gather_rank = rank;       /* so that gather_close releases what was opened */
+      gather_close(ctx);
+      return fail(ctx, DPGICP_E_CUDA, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(g) + "): " + cudaGetErrorString(e));
+    }
+    ctx->gather_peer[g] = p;
+  }
+  ctx->gather_world = world;
+  ctx->gather_rank = rank;
+  return DPGICP_OK;
+}
+
+int dpgicp_gather_detach(dpgicp_ctx *ctx) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return gather_close(ctx);
+}
+
+int dpgicp_gather_fetch(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n < 0 || n > ctx->gather_n || (n > 0 && !out)) return fail(ctx, DPGICP_E_INVALID, "bad fetch arguments");
+  if (n > 0)
+    CU_TRY(ctx, cudaMemcpyAsync(out, ctx->gather.p, sizeof(dpgicp_result) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
+}
+
+int dpgicp_gather_device_ptr(dpgicp_ctx *ctx, void **out_ptr, int64_t *out_n) {
+  if (!ctx || !out_ptr || !out_n) return DPGICP_E_INVALID;
+  *out_ptr = ctx->gather.p;
+  *out_n = ctx->gather_n;
   return DPGICP_OK;
 }
 

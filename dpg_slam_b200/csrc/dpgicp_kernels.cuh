@@ -95,6 +95,11 @@ struct KernelParams {
   long long *susp_out;
   unsigned char *state_out;
   long long slot_bytes;               /* kStateHeader + 12 * n_cap                                 */
+  /* multi-GPU gather fused into the epilogue: with gather_world > 1 the record of local pair k also goes to
+   * slot (gather_rank + k * gather_world) of EVERY rank's gather buffer — peer-mapped device memory, written
+   * with plain stores over NVLink; no collective is launched                                              */
+  dpgicp_result *gather_peer[DPGICP_MAX_GATHER_RANKS];
+  int32_t gather_world, gather_rank;
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -952,6 +957,16 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       }
       r.status = status | cov_flag;
       P.results[pair] = r;
+      if (P.gather_world > 1) {
+        /* fused gather: seven 16-byte stores per peer, straight into every rank's buffer at the global slot */
+        const long long slot = (long long)P.gather_rank + pair * (long long)P.gather_world;
+        const int4 *src = reinterpret_cast<const int4 *>(&r);
+        for (int g = 0; g < P.gather_world; ++g) {
+          int4 *dst = reinterpret_cast<int4 *>(P.gather_peer[g] + slot);
+#pragma unroll
+          for (int q = 0; q < (int)(sizeof(dpgicp_result) / 16); ++q) dst[q] = src[q];
+        }
+      }
     }
   }
 

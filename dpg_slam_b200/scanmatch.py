@@ -189,6 +189,28 @@ class ScanMatcher:
         self._check(self._lib.dpgicp_results_device_ptr(self._h, C.byref(p), C.byref(n)))
         return int(p.value or 0), int(n.value)
 
+    # ---- multi-GPU gather fused into the kernel epilogue (peer stores over NVLink) ------------------------------
+    def gather_export(self, n_global_pairs: int) -> bytes:
+        """Allocate this rank's buffer for the WHOLE batch's records; returns its 64-byte CUDA IPC handle."""
+        h = (C.c_ubyte * _abi.IPC_HANDLE_BYTES)()
+        self._check(self._lib.dpgicp_gather_export(self._h, n_global_pairs, C.byref(h)))
+        return bytes(h)
+
+    def gather_attach(self, handles, rank: int):
+        """``handles``: every rank's exported handle, in rank order.  From now on ``run`` stores record k of the
+        local shard into slot ``rank + k * world`` of every rank's buffer."""
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.dpgicp_gather_attach(self._h, C.byref(buf), len(handles), rank))
+
+    def gather_detach(self):
+        self._check(self._lib.dpgicp_gather_detach(self._h))
+
+    def gather_fetch(self, n_global_pairs: int) -> np.ndarray:
+        out = np.zeros(n_global_pairs, RESULT_DTYPE)
+        self._check(self._lib.dpgicp_gather_fetch(self._h, out.ctypes.data, n_global_pairs))
+        return out
+
     def last_run_counters(self) -> dict:
         c = (C.c_uint64 * 8)()
         self._check(self._lib.dpgicp_last_run_counters(self._h, C.byref(c)))

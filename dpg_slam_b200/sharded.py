@@ -98,6 +98,7 @@ class ShardedScanMatcher:
         self.n_pairs = 0
         self._send = self._recv = None
         self._remap = None
+        self._fused = 0
 
     def plan_subset(self, src_idx, tgt_idx, n_scans_total: int) -> np.ndarray:
         """The distinct scans this rank's pairs touch (ascending) — the rows of a per-rank store — and the
@@ -152,6 +153,33 @@ class ShardedScanMatcher:
                                                    non_blocking=True)
         dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
         return self._recv
+
+    # ---- gather fused into the kernel: no collective on the data path ----------------------------------------
+    def attach_fused_gather(self, n_global_pairs: int):
+        """Exchange CUDA IPC handles of per-rank whole-batch buffers once; afterwards every ``run`` writes its
+        records straight into all ranks' buffers from the kernel epilogue (peer stores over NVLink)."""
+        import torch.distributed as dist
+        mine = self.sm.gather_export(n_global_pairs)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=self.group)
+        self.sm.gather_attach(handles, self.rank)
+        self._fused = int(n_global_pairs)
+        dist.barrier(group=self.group)
+
+    def detach_fused_gather(self):
+        import torch.distributed as dist
+        self.sm.synchronize()
+        dist.barrier(group=self.group)        # nobody may still be storing into a buffer that is about to close
+        self.sm.gather_detach()
+        self._fused = 0
+
+    def fused_records(self) -> np.ndarray:
+        """All records in global pair order from this rank's own buffer.  Synchronises this rank's stream and
+        then all ranks (a peer's stores are complete once its kernel has finished)."""
+        import torch.distributed as dist
+        self.sm.synchronize()
+        dist.barrier(group=self.group)
+        return self.sm.gather_fetch(self.n_pairs)
 
     def gather(self) -> np.ndarray:
         """All ``n_pairs`` records in global pair order, on the host, on every rank."""

@@ -177,6 +177,23 @@ int  dpgicp_fetch_factors(dpgicp_ctx *ctx, dpgicp_factor *out, int64_t n_pairs);
 /* device address of the record array written by dpgicp_run (n_pairs * sizeof(dpgicp_result));
  * lets a multi-GPU host gather records device-to-device (NCCL) without a host bounce.          */
 int  dpgicp_results_device_ptr(dpgicp_ctx *ctx, void **out_ptr, int64_t *out_n_pairs);
+/* ---- multi-GPU gather fused into the kernel (one context per GPU, one process per GPU or not) --------------
+ * Scan pairs are independent, so pair k of a global batch runs on rank k % world (round-robin) and the ONLY
+ * exchange is the gather of the records.  Instead of a collective after the kernel, every rank exports a buffer
+ * sized for the whole batch (CUDA IPC handle, 64 bytes), attaches all ranks' buffers, and from then on dpgicp_run
+ * stores each finished record straight into slot (rank + k * world) of every rank's buffer (peer stores over
+ * NVLink from the kernel's epilogue).  After all ranks have synchronised, every buffer holds the whole batch in
+ * global pair order.                                                                                       */
+#define DPGICP_IPC_HANDLE_BYTES   64
+#define DPGICP_MAX_GATHER_RANKS   16
+int  dpgicp_gather_export(dpgicp_ctx *ctx, int64_t n_global_pairs, unsigned char handle_out[DPGICP_IPC_HANDLE_BYTES]);
+/* handles = world * 64 bytes in rank order (this rank's own entry is ignored and may be anything) */
+int  dpgicp_gather_attach(dpgicp_ctx *ctx, const unsigned char *handles, int32_t world, int32_t rank);
+int  dpgicp_gather_detach(dpgicp_ctx *ctx);
+/* copy the first n records of this rank's gather buffer to the host (caller has synchronised all ranks) */
+int  dpgicp_gather_fetch(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n_global_pairs);
+int  dpgicp_gather_device_ptr(dpgicp_ctx *ctx, void **out_ptr, int64_t *out_n_global_pairs);
+
 /* executed-work counters of the last dpgicp_run, summed over pairs (after synchronisation):
  * [0] iterations, [1] correspondences, [2] distance evaluations, [3] block tests, [4] kernel launches */
 int  dpgicp_last_run_counters(dpgicp_ctx *ctx, uint64_t counters[8]);

@@ -38,7 +38,15 @@ def _worker(rank, world, port, n_pairs, q):
             sh = sharded.ShardedScanMatcher(sm, rank, world, None, dev)
             sh.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)          # pair k -> rank k % world
             sh.run(p)
-            allrec = sh.gather()
+            allrec = sh.gather()                                    # NCCL all-gather of the records
+            # the same gather fused into the kernel epilogue: peer stores into every rank's buffer, no collective
+            sh.attach_fused_gather(n_pairs)
+            sh.run(p)
+            fused = sh.fused_records()
+            sh.run(p)                                               # buffers are reusable batch after batch
+            fused2 = sh.fused_records()
+            sh.detach_fused_gather()
+            assert fused.tobytes() == allrec.tobytes() and fused2.tobytes() == allrec.tobytes()
             single = None
             if rank == 0:
                 sm.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
