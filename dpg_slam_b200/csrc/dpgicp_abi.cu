@@ -54,13 +54,13 @@ struct dpgicp_ctx {
   Batch batch, scratch_batch;
   DevBuf stage, offsets, misc, corr;
   DevBuf state[2], susp[2];                  /* suspended-pair state slots + pair lists, ping-pong between stages */
-  unsigned long long *d_queue = nullptr;     /* [0..2] stage queue heads, [4],[5] suspended counts, [8..15] counters */
+  unsigned long long *d_queue = nullptr;     /* [0..4] stage queue heads, [6],[7] suspended counts, [8..15] counters, [16..23] development phase timers */
   DevBuf gather;                             /* this rank's copy of the whole batch's records (fused gather)  */
   int64_t gather_n = 0;
   int gather_world = 0, gather_rank = 0;
   void *gather_peer[DPGICP_MAX_GATHER_RANKS] = {nullptr};
-  int max_stages = 4;
-  std::vector<int> chain;                    /* DPGICP_CHAIN: target warps per stage (development knob) */
+  int max_stages = 5;
+  std::vector<int> chain, chain_cluster;     /* DPGICP_CHAIN: target warps (and "x<cluster size>") per stage (development knob) */
   int *d_bad = nullptr;
   void *h_stage = nullptr;                   /* pinned staging for subset uploads from pageable memory */
   size_t h_stage_cap = 0;
@@ -126,49 +126,74 @@ float gate_threshold(const dpgicp_params *p) {
   return f;
 }
 
-template <int WARPS, bool PRUNED>
+template <int WARPS, bool PRUNED, int CSIZE>
 int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t max_items, int nw, int *grid_out) {
-  auto kern = icp_pairs_kernel<WARPS, PRUNED>;
+  auto kern = icp_pairs_kernel<WARPS, PRUNED, CSIZE>;
   CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nw * 32, smem));
-  if (per_sm < 1) return fail(ctx, DPGICP_E_TOOBIG, "scan too large for one CTA's shared memory");
-  if (ctx->force_ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->force_ctas_per_sm);
-  /* persistent grid: a whole number of resident CTAs per SM, never more CTAs than work items */
-  int64_t grid = (int64_t)ctx->sm_count * per_sm;
-  if (grid > max_items) grid = max_items;
-  if (grid < 1) grid = 1;
-  if (grid_out) {
-    if (*grid_out < 0) { *grid_out = (int)grid; return DPGICP_OK; }      /* query only */
-    *grid_out = (int)grid;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3((unsigned)nw * 32, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CSIZE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CSIZE > 1 ? 1 : 0;
+  int64_t units = 0;                        /* resident CTAs (CSIZE == 1) or clusters on the whole device */
+  if (CSIZE > 1) {
+    cfg.gridDim = dim3((unsigned)(ctx->sm_count / CSIZE) * CSIZE, 1, 1);
+    int n_clusters = 0;
+    CU_TRY(ctx, cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
+    if (n_clusters < 1) return fail(ctx, DPGICP_E_TOOBIG, "no cluster of this shape fits the device");
+    units = n_clusters;
+  } else {
+    int per_sm = 0;
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nw * 32, smem));
+    if (per_sm < 1) return fail(ctx, DPGICP_E_TOOBIG, "scan too large for one CTA's shared memory");
+    if (ctx->force_ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->force_ctas_per_sm);
+    units = (int64_t)ctx->sm_count * per_sm;
   }
-  kern<<<(unsigned)grid, nw * 32, smem, ctx->stream>>>(kp);
+  /* persistent grid: a whole number of resident CTAs per SM (or clusters), never more than work items */
+  if (units > max_items) units = max_items;
+  if (units < 1) units = 1;
+  const int64_t grid = units * CSIZE;
+  if (grid_out) {
+    if (*grid_out < 0) { *grid_out = (int)units; return DPGICP_OK; }      /* query only */
+    *grid_out = (int)units;
+  }
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  CU_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, kp));
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   return DPGICP_OK;
 }
 
-/* nw warps per CTA run on the instantiation with the next power-of-two register budget */
+/* nw warps per CTA run on the instantiation with the next power-of-two register budget; clusters (the last
+ * stage only) use the 16-warp budget */
 template <bool PRUNED>
-int launch_icp_w(dpgicp_ctx *ctx, int nw, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
-  if (nw <= 1) return launch_icp_t<1, PRUNED>(ctx, kp, smem, n, 1, grid_out);
-  if (nw <= 2) return launch_icp_t<2, PRUNED>(ctx, kp, smem, n, nw, grid_out);
-  if (nw <= 4) return launch_icp_t<4, PRUNED>(ctx, kp, smem, n, nw, grid_out);
-  if (nw <= 8) return launch_icp_t<8, PRUNED>(ctx, kp, smem, n, nw, grid_out);
-  if (nw <= 16) return launch_icp_t<16, PRUNED>(ctx, kp, smem, n, nw, grid_out);
-  return launch_icp_t<32, PRUNED>(ctx, kp, smem, n, std::min(nw, 32), grid_out);
+int launch_icp_w(dpgicp_ctx *ctx, int nw, int csize, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
+  nw = std::max(1, std::min(nw, 16));
+  if (csize == 2) return launch_icp_t<16, PRUNED, 2>(ctx, kp, smem, n, nw, grid_out);
+  if (csize == 4) return launch_icp_t<16, PRUNED, 4>(ctx, kp, smem, n, nw, grid_out);
+  if (nw <= 1) return launch_icp_t<1, PRUNED, 1>(ctx, kp, smem, n, 1, grid_out);
+  if (nw <= 2) return launch_icp_t<2, PRUNED, 1>(ctx, kp, smem, n, nw, grid_out);
+  if (nw <= 4) return launch_icp_t<4, PRUNED, 1>(ctx, kp, smem, n, nw, grid_out);
+  if (nw <= 8) return launch_icp_t<8, PRUNED, 1>(ctx, kp, smem, n, nw, grid_out);
+  return launch_icp_t<16, PRUNED, 1>(ctx, kp, smem, n, nw, grid_out);
 }
 
-int launch_stage(dpgicp_ctx *ctx, bool pruned, int nw, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
-  return pruned ? launch_icp_w<true>(ctx, nw, kp, smem, n, grid_out) : launch_icp_w<false>(ctx, nw, kp, smem, n, grid_out);
+int launch_stage(dpgicp_ctx *ctx, bool pruned, int nw, int csize, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
+  return pruned ? launch_icp_w<true>(ctx, nw, csize, kp, smem, n, grid_out) : launch_icp_w<false>(ctx, nw, csize, kp, smem, n, grid_out);
 }
 
 /* warps per CTA close to `target` that split `tiles` 32-point tiles evenly (every warp gets
  * ceil(tiles / nw) or one fewer): 34 tiles -> 4, 7, 12, 17 for targets 4, 8, 16, 32 */
-int balanced_warps(int tiles, int target) {
-  target = std::max(1, std::min(32, target));
-  const int per_warp = (tiles + target - 1) / target;
-  return std::max(1, (tiles + per_warp - 1) / per_warp);
+int balanced_warps(int tiles, int target, int csize = 1) {
+  target = std::max(1, std::min(16, target));
+  const int slots = target * csize;
+  const int per_warp = (tiles + slots - 1) / slots;
+  const int warps_total = (tiles + per_warp - 1) / per_warp;
+  return std::max(1, (warps_total + csize - 1) / csize);
 }
 
 int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_params *p, int32_t *corr_out,
@@ -217,20 +242,25 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   const int tiles = n_cap / kTile;
   int w0 = ctx->force_warps;
   if (w0 <= 0) w0 = n_cap <= 512 ? 2 : (n_cap <= 2048 ? 4 : 8);
-  int targets[4] = {w0, 2 * w0, 16, 16};       /* measured on B200: 34 tiles -> 4, 7, 12 warps; a 17-warp CTA (64 registers
-                                                * per thread) is no faster per pass than 12 warps                         */
-  int n_targets = 3;
+  struct StageShape { int warps, csize; };
+  /* 34 tiles (1081 beams) -> 4, 7, 12 warps per CTA, then clusters of 4 CTAs x 9 warps (one tile per warp on four
+   * SMs) for the last pairs: measured per-pass latency of one pair 28.7 / 17.9 / 11.4 / 6.3 us */
+  StageShape targets[5] = {{w0, 1}, {2 * w0, 1}, {16, 1}, {16, 4}, {16, 1}};
+  int n_targets = tiles >= 16 ? 4 : 3;
   if (!ctx->chain.empty()) {
     n_targets = 0;
-    for (int w : ctx->chain) if (n_targets < 4) targets[n_targets++] = w;
+    for (size_t k = 0; k < ctx->chain.size() && n_targets < 5; ++k)
+      targets[n_targets++] = {ctx->chain[k], ctx->chain_cluster[k]};
   }
-  int widths[4] = {balanced_warps(tiles, targets[0]), 0, 0, 0};
+  StageShape shapes[5] = {{balanced_warps(tiles, targets[0].warps), 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}};
   int n_stages = 1;
   if (corr_out == nullptr) {
     for (int k = 1; k < n_targets && n_stages < ctx->max_stages; ++k) {
-      const int w = balanced_warps(tiles, targets[k]);
-      if (w <= widths[n_stages - 1]) continue;
-      widths[n_stages++] = w;
+      /* a cluster of CTAs per pair is only used for the last stage (it never suspends) */
+      const int cs = (k + 1 == n_targets || n_stages + 1 == ctx->max_stages) ? targets[k].csize : 1;
+      const int w = balanced_warps(tiles, targets[k].warps, cs);
+      if (w * cs <= shapes[n_stages - 1].warps * shapes[n_stages - 1].csize) continue;
+      shapes[n_stages++] = {w, cs};
     }
   }
   CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, 24 * sizeof(unsigned long long), ctx->stream));
@@ -238,7 +268,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   if (n_stages > 1) {
     /* every stage can suspend at most one pair per CTA: size the state slots for stage 0's grid */
     int g0 = -1;
-    int rc = launch_stage(ctx, pruned, widths[0], kp, smem, b.n_pairs, &g0);
+    int rc = launch_stage(ctx, pruned, shapes[0].warps, shapes[0].csize, kp, smem, b.n_pairs, &g0);
     if (rc) return rc;
     for (int k = 0; k < 2; ++k) {
       if ((rc = reserve(ctx, ctx->state[k], (size_t)g0 * (size_t)kp.slot_bytes))) return rc;
@@ -250,20 +280,20 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
     ks.queue = ctx->d_queue + sidx;
     ks.resume = sidx > 0 ? 1 : 0;
     if (sidx > 0) {
-      ks.in_count = reinterpret_cast<const unsigned int *>(ctx->d_queue + 4 + ((sidx - 1) & 1));
+      ks.in_count = reinterpret_cast<const unsigned int *>(ctx->d_queue + 6 + ((sidx - 1) & 1));
       ks.susp_in = (const long long *)ctx->susp[(sidx - 1) & 1].p;
       ks.state_in = (const unsigned char *)ctx->state[(sidx - 1) & 1].p;
     }
     if (sidx + 1 < n_stages) {
-      ks.out_count = reinterpret_cast<unsigned int *>(ctx->d_queue + 4 + (sidx & 1));
+      ks.out_count = reinterpret_cast<unsigned int *>(ctx->d_queue + 6 + (sidx & 1));
       ks.susp_out = (long long *)ctx->susp[sidx & 1].p;
       ks.state_out = (unsigned char *)ctx->state[sidx & 1].p;
       if (sidx >= 2)      /* the count cell is reused by stage sidx: clear it after stage sidx-1 consumed it */
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue + 4 + (sidx & 1), 0, sizeof(unsigned long long), ctx->stream));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue + 6 + (sidx & 1), 0, sizeof(unsigned long long), ctx->stream));
     }
     int grid = 0;
     const int64_t max_items = sidx == 0 ? b.n_pairs : (int64_t)grid_prev;
-    int rc = launch_stage(ctx, pruned, widths[sidx], ks, smem, max_items, &grid);
+    int rc = launch_stage(ctx, pruned, shapes[sidx].warps, shapes[sidx].csize, ks, smem, max_items, &grid);
     if (rc) return rc;
     grid_prev = grid;
   }
@@ -451,11 +481,13 @@ int dpgicp_create(int device, dpgicp_ctx **out) {
   }
   if (const char *w = std::getenv("DPGICP_WARPS")) ctx->force_warps = std::atoi(w);
   if (const char *c = std::getenv("DPGICP_CTAS_PER_SM")) ctx->force_ctas_per_sm = std::atoi(c);
-  if (const char *c = std::getenv("DPGICP_STAGES")) ctx->max_stages = std::max(1, std::min(4, std::atoi(c)));
+  if (const char *c = std::getenv("DPGICP_STAGES")) ctx->max_stages = std::max(1, std::min(5, std::atoi(c)));
   if (const char *c = std::getenv("DPGICP_CHAIN")) {
-    for (const char *q = c; *q;) {
+    for (const char *q = c; *q;) {            /* e.g. "4,8,16,9x2": the last stage as clusters of 2 CTAs x 9 warps */
       ctx->chain.push_back(std::max(1, std::atoi(q)));
-      while (*q && *q != ',') ++q;
+      int cs = 1;
+      while (*q && *q != ',') { if (*q == 'x') cs = std::atoi(q + 1); ++q; }
+      ctx->chain_cluster.push_back(cs == 2 || cs == 4 ? cs : 1);
       if (*q == ',') ++q;
     }
   }

@@ -26,6 +26,7 @@
  */
 #pragma once
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -200,7 +201,7 @@ struct SmemLayout {
   float4 *sbox;     /* n_cap/kGroup group boxes of the current source                                */
   float4 *stile;    /* n_cap/32 boxes of the source tiles (query boxes of the forward search)        */
   int32_t *tcnt;    /* n_cap/32 accepted per source tile (rank for the covariance cap)              */
-  long long *red;   /* 16 int64 moment sums                                                         */
+  long long *red;   /* 48 int64: [0..15] totals of the pass, [16..47] this CTA's totals by pass parity (clusters) */
   double *dpart;    /* kMaxWarps * 12 partial double sums (deterministic order)                     */
   float *step;      /* 4 */
   int32_t *ctl;     /* [0] item lo [1] item hi [2] stop [3] K [4] slot                               */
@@ -209,7 +210,7 @@ struct SmemLayout {
 
 __host__ __device__ inline size_t smem_bytes(int n_cap) {
   const int g = n_cap / kGroup, t = n_cap / kTile;
-  return (size_t)n_cap * (8 + 8 + 4) + (size_t)g * (16 + 16) + (size_t)t * (16 + 4) + 16 * 8 + kMaxWarps * 12 * 8 + 16 + 32 +
+  return (size_t)n_cap * (8 + 8 + 4) + (size_t)g * (16 + 16) + (size_t)t * (16 + 4) + 48 * 8 + kMaxWarps * 12 * 8 + 16 + 32 +
          16 + 64;
 }
 
@@ -223,7 +224,7 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap) {
   L.tbox = (float4 *)(base + o); o += (size_t)g * 16;
   L.sbox = (float4 *)(base + o); o += (size_t)g * 16;
   L.stile = (float4 *)(base + o); o += (size_t)t * 16;
-  L.red = (long long *)(base + o); o += 16 * 8;
+  L.red = (long long *)(base + o); o += 48 * 8;
   L.dpart = (double *)(base + o);  o += kMaxWarps * 12 * 8;
   L.mbar = (uint64_t *)(base + o); o += 16;
   L.tcnt = (int32_t *)(base + o); o += (size_t)t * 4;
@@ -556,14 +557,35 @@ __host__ __device__ constexpr int min_ctas(int warps) {
   return (DPGICP_TARGET_WARPS / warps) < 1 ? 1 : (DPGICP_TARGET_WARPS / warps) > 16 ? 16 : (DPGICP_TARGET_WARPS / warps);   /* 16, 17, 32 -> 1 */
 }
 
-template <int WARPS, bool PRUNED>
+/* CSIZE > 1: a thread-block CLUSTER of CSIZE CTAs (one per SM) works on one pair — used by the host for the
+ * last stage of the chain, where a few long pairs are all that is left and one SM cannot run a pass faster
+ * (it is bound by its issue rate).  Every CTA of the cluster stages both clouds in its own shared memory and
+ * keeps them identical (each applies every step to all source points — redundant but exact); the search
+ * tiles are split over the CTAs; the per-warp partial sums of all CTAs are read through distributed shared
+ * memory after one cluster barrier per pass, so every CTA forms the same exact integer totals and takes the
+ * same step and the same stop decision without any broadcast.  CTA 0 writes the record. */
+template <int CSIZE>
+__device__ __forceinline__ void pair_sync() {
+  if constexpr (CSIZE > 1) cooperative_groups::this_cluster().sync();
+  else __syncthreads();
+}
+template <int CSIZE, typename T>
+__device__ __forceinline__ T *peer_smem(T *p, int rank) {
+  if constexpr (CSIZE > 1) return cooperative_groups::this_cluster().map_shared_rank(p, rank);
+  else return p;
+}
+
+template <int WARPS, bool PRUNED, int CSIZE>
 __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(const KernelParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SmemLayout L = carve(smem_raw, P.n_cap);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nw = blockDim.x >> 5;            /* warps of this CTA: <= WARPS, chosen by the host so that
-                                              * the pair's tiles divide evenly among them            */
+  const int nw = blockDim.x >> 5;            /* warps of this CTA: <= WARPS (and <= 16), chosen by the host so
+                                              * that the pair's tiles divide evenly among them                 */
   const int nthreads = blockDim.x;
+  int crank = 0;                             /* rank of this CTA in its cluster                                */
+  if constexpr (CSIZE > 1) crank = (int)cooperative_groups::this_cluster().block_rank();
+  const int tile0 = crank * nw + warp, tile_stride = nw * CSIZE;     /* search tiles of this warp             */
   const int div = P.divisor;
   constexpr int GPT = kTile / kGroup;        /* groups per tile */
   uint32_t mbar_phase = 0;
@@ -578,12 +600,15 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
 
   for (;;) {
     /* ---- fetch the next work item ----------------------------------------------------------- */
-    if (tid == 0) {
+    if (tid == 0 && crank == 0) {
       const unsigned long long k = atomicAdd(P.queue, 1ull);
-      L.ctl[0] = (int32_t)(k & 0xffffffffu);
-      L.ctl[1] = (int32_t)(k >> 32);
+      for (int r = 0; r < CSIZE; ++r) {               /* every CTA of the cluster works on the same item */
+        int32_t *c = peer_smem<CSIZE>(L.ctl, r);
+        c[0] = (int32_t)(k & 0xffffffffu);
+        c[1] = (int32_t)(k >> 32);
+      }
     }
-    __syncthreads();
+    pair_sync<CSIZE>();
     const unsigned long long item = ((unsigned long long)(uint32_t)L.ctl[1] << 32) | (uint32_t)L.ctl[0];
     if (item >= n_items) break;
     const long long pair = P.resume ? P.susp_in[item] : (long long)item;
@@ -665,6 +690,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
     }
 
     int stop = 0;
+    int parity = 0;                       /* the partial-sum slots are double-buffered by pass parity: peers may
+                                           * still be reading the previous pass's slots                         */
 #ifdef DPGICP_PHASE_TIMING
     long long ph[6] = {0, 0, 0, 0, 0, 0};
 #define PH_MARK(k) do { if (tid == 0) { const long long now__ = clock64(); ph[k] += now__ - ph_t; ph_t = now__; } } while (0)
@@ -675,7 +702,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
     for (;;) {
       long long m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, m6 = 0, m7 = 0, m8 = 0, m_d2 = 0;
       int m_k = 0;
-      for (int tile = warp; tile < ts; tile += nw) {
+      for (int tile = tile0; tile < ts; tile += tile_stride) {
         float2 q; int j; float d; bool fwd;
         const bool acc = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
                                             stats);
@@ -746,24 +773,47 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       if (lane == 0) {
         /* per-warp partials in shared memory (plain stores; a 64-bit shared atomicAdd is a CAS spin loop);
          * the slots alias L.dpart, which is only used by the covariance after the pass loop */
-        long long *w = reinterpret_cast<long long *>(L.dpart) + warp * 12;
+        long long *w = reinterpret_cast<long long *>(L.dpart) + (parity * 16 + warp) * 12;
         w[0] = m0; w[1] = m1; w[2] = m2; w[3] = m3; w[4] = m4; w[5] = m5; w[6] = m6; w[7] = m7; w[8] = m8;
         w[9] = m_d2; w[10] = (long long)m_k;
       }
-      PH_MARK(1);                                     /* warp reduction + shared atomics */
-      __syncthreads();
+      PH_MARK(1);                                     /* warp reduction + partial slots */
+      __syncthreads();                                /* all warps of this CTA have stored */
       PH_MARK(2);                                     /* wait for the other warps */
 
-      if (warp == 0) {
+      if constexpr (CSIZE > 1) {
+        /* cluster: each CTA first folds its own warps into one set of 11 totals, so that a peer reads
+         * 11 values per CTA through distributed shared memory (latency ~200 cycles each), not 11 per warp */
+        if (warp == 0 && lane < 11) {
+          const long long *w = reinterpret_cast<const long long *>(L.dpart) + parity * 16 * 12 + lane;
+          long long tot = 0;
+          for (int q = 0; q < nw; ++q) tot += w[q * 12];
+          L.red[16 + parity * 16 + lane] = tot;
+        }
+        pair_sync<CSIZE>();                           /* every CTA of the pair has published its totals */
+        if (warp == 0) {
+          if (lane < 11) {
+            long long v[CSIZE];
+#pragma unroll
+            for (int r = 0; r < CSIZE; ++r) v[r] = peer_smem<CSIZE>(L.red, r)[16 + parity * 16 + lane];
+            long long tot = 0;
+#pragma unroll
+            for (int r = 0; r < CSIZE; ++r) tot += v[r];
+            L.red[lane] = tot;
+          }
+          __syncwarp();
+        }
+      } else if (warp == 0) {
         /* exact integer totals: lane k adds value k over the warps (any order gives the same bits) */
         if (lane < 11) {
-          const long long *w = reinterpret_cast<const long long *>(L.dpart) + lane;
+          const long long *w = reinterpret_cast<const long long *>(L.dpart) + parity * 16 * 12 + lane;
           long long tot = 0;
           for (int q = 0; q < nw; ++q) tot += w[q * 12];
           L.red[lane] = tot;
         }
         __syncwarp();
       }
+      parity ^= 1;
       if (tid == 0) {
         /* has this stage's queue run dry?  (read early, the L2 round trip overlaps the solve) */
         unsigned long long qhead = 0;
@@ -816,7 +866,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       PH_MARK(3);                                     /* solve + convergence */
       __syncthreads();
       stop = L.ctl[2];
-      c_corr += (tid == 0) ? (unsigned long long)L.ctl[3] : 0ull;
+      c_corr += (tid == 0 && crank == 0) ? (unsigned long long)L.ctl[3] : 0ull;
       if (stop == 2) break;
       /* src' = step * src' in place (App. A.3-6) and refresh the source boxes */
       {
@@ -828,7 +878,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
         }
       }
-      if (tid == 0) ++c_iters;
+      if (tid == 0 && crank == 0) ++c_iters;
       PH_MARK(4);                                     /* transform + boxes (own tiles) */
       __syncthreads();
       PH_MARK(5);                                     /* wait */
@@ -864,6 +914,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
     for (int k = 0; k < 11; ++k) S[k] = 0.0;
     uint32_t cov_flag = 0;
     const int cov_mode = P.cov_mode;
+    if constexpr (CSIZE > 1) pair_sync<CSIZE>();     /* peers have finished reading this CTA's partial-sum slots */
     if (cov_mode != DPGICP_COV_REFERENCE_LIVE) {
       /* pose as cov.h:26-35: x,y float entries widened, a = (double)atan2f(T10, T00); all threads */
       if (tid == 0) { L.step[0] = fc; L.step[1] = fs; L.step[2] = ftx; L.step[3] = fty; }
@@ -888,7 +939,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
         }
         __syncthreads();
-        for (int tile = warp; tile < ts; tile += nw) {
+        for (int tile = tile0; tile < ts; tile += tile_stride) {
           float2 q; int j; float d; bool fwd;
           const bool ok = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
                                              stats);
@@ -897,13 +948,16 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           if (i < ns) L.nn[i] = ok ? j : -1;
           if (lane == 0) L.tcnt[tile] = __popc(bal);
         }
-        __syncthreads();
+        pair_sync<CSIZE>();
         n_cov = ns;
       }
       const int cov_tiles = (n_cov + kTile - 1) / kTile;
       for (int chunk = 0; chunk < cov_tiles; chunk += kCovChunk) {
         const int chunk_end = chunk + kCovChunk < cov_tiles ? chunk + kCovChunk : cov_tiles;
-        for (int tile = chunk + warp; tile < chunk_end; tile += nw) {
+        /* tile t belongs to CTA (t / nw) % CSIZE, warp t % nw — the same split as the search tiles */
+        int tile_first = tile0;
+        if (tile_first < chunk) tile_first += ((chunk - tile_first + tile_stride - 1) / tile_stride) * tile_stride;
+        for (int tile = tile_first; tile < chunk_end; tile += tile_stride) {
           double acc[11];
 #pragma unroll
           for (int k = 0; k < 11; ++k) acc[k] = 0.0;
@@ -915,7 +969,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
             }
           } else {
             int prefix = 0;
-            for (int t = lane; t < tile; t += 32) prefix += L.tcnt[t];
+            for (int t = lane; t < tile; t += 32) prefix += peer_smem<CSIZE>(L.tcnt, (t / nw) % CSIZE)[t];
             prefix = __reduce_add_sync(0xffffffffu, prefix);
             const int j = (i < ns) ? L.nn[i] : -1;
             const unsigned bal = __ballot_sync(0xffffffffu, j >= 0);
@@ -932,15 +986,17 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           if (lane == 0)
             for (int k = 0; k < 11; ++k) L.dpart[(tile - chunk) * 12 + k] = acc[k];
         }
-        __syncthreads();
-        if (tid == 0)
-          for (int t = 0; t < chunk_end - chunk; ++t)
-            for (int k = 0; k < 11; ++k) S[k] = __dadd_rn(S[k], L.dpart[t * 12 + k]);
-        __syncthreads();
+        pair_sync<CSIZE>();
+        if (tid == 0 && crank == 0)
+          for (int t = 0; t < chunk_end - chunk; ++t) {
+            const double *dp = peer_smem<CSIZE>(L.dpart, ((chunk + t) / nw) % CSIZE) + t * 12;
+            for (int k = 0; k < 11; ++k) S[k] = __dadd_rn(S[k], dp[k]);
+          }
+        pair_sync<CSIZE>();
       }
     }
 
-    if (tid == 0) {
+    if (tid == 0 && crank == 0) {
       dpgicp_result r;
       r.tx = ftx; r.ty = fty;
       r.theta = atan2f(fs, fc);                      /* Rotation2Df::fromRotationMatrix().angle() */
@@ -969,6 +1025,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       }
     }
   }
+
+  if constexpr (CSIZE > 1) pair_sync<CSIZE>();       /* no CTA leaves while a peer may still address its shared memory */
 
   /* executed-work counters (one set of atomics per CTA) */
   if (lane == 0) {

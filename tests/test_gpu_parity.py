@@ -426,6 +426,12 @@ def test_full_size_batch_properties(gpu_matcher):
     assert np.median(np.abs(got["ty"] - wl.truth[:, 1])) < 2e-2
 
 
+def gpu_matcher_records(gpu_matcher, wl, p):
+    """records from the session-wide matcher (default chain, created before any env override)"""
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    return gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+
+
 def test_staged_chain_equals_single_stage(gpu_matcher, monkeypatch):
     """The kernel runs as a chain of stages (narrow CTAs first; pairs still running when a stage's queue
     runs dry are suspended to HBM and resumed by wider CTAs).  Suspension restores state bit for bit,
@@ -436,7 +442,9 @@ def test_staged_chain_equals_single_stage(gpu_matcher, monkeypatch):
     gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
     want = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
     for stages, warps, chain in ((1, 4, None), (2, 2, None), (3, 1, None), (3, 8, None), (1, 16, None), (4, 0, "3,5,11,32"),
-                                 (4, 0, "4,8,16,32"), (2, 0, "1,32"), (1, 32, None)):
+                                 (4, 0, "4,8,16,32"), (2, 0, "1,32"), (1, 32, None),
+                                 # last stage as thread-block clusters: 2 or 4 CTAs (SMs) per pair, partial sums through DSMEM
+                                 (4, 0, "4,8,16,9x2"), (3, 0, "4,8,9x4"), (2, 0, "2,5x2"), (2, 0, "4,16x4")):
         monkeypatch.setenv("DPGICP_STAGES", str(stages))
         monkeypatch.setenv("DPGICP_WARPS", str(warps))
         if chain:
@@ -458,6 +466,23 @@ def test_staged_chain_equals_single_stage(gpu_matcher, monkeypatch):
     with ScanMatcher(0) as sm:
         sm.upload_ranges(wl.ranges, wl.scanner)
         assert sm.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p5).tobytes() == want5.tobytes()
+    # clusters with every covariance mode and metric, ragged and empty scans, small batches (all pairs reach the cluster stage)
+    monkeypatch.setenv("DPGICP_STAGES", "4")
+    monkeypatch.setenv("DPGICP_WARPS", "0")
+    wl2 = synth.config_corridor(n_pairs=40, n_beams=721, seed=12)
+    wl2.ranges[2, :] = 40.0
+    wl2.ranges[4, 2:] = 40.0
+    wl2.ranges[6, ::2] = 40.0
+    for chain in ("4,8,9x2", "2,6x4"):
+        monkeypatch.setenv("DPGICP_CHAIN", chain)
+        with ScanMatcher(0) as sm:
+            sm.upload_ranges(wl2.ranges, wl2.scanner)
+            for cov_mode in (COV_REFERENCE_LIVE, COV_CENSI_INDEXPAIR, COV_CENSI_CORR):
+                for metric, div in ((0, 1), (METRIC_POINT_TO_LINE, 1), (0, 5)):
+                    pc = Params.defaults(downsample_divisor=div, cov_mode=cov_mode, metric=metric)
+                    got = sm.submit_pairs(wl2.src_idx, wl2.tgt_idx, wl2.guess, pc)
+                    ref = gpu_matcher_records(gpu_matcher, wl2, pc)
+                    assert got.tobytes() == ref.tobytes(), (chain, cov_mode, metric, div)
 
 
 def test_rotation_entries_stay_orthonormal(gpu_matcher):
