@@ -52,7 +52,9 @@ struct dpgicp_ctx {
   bool own_stream = true;
   Store store, scratch_store;
   Batch batch, scratch_batch;
-  DevBuf stage, offsets, misc, corr;
+  DevBuf stage, offsets, misc, corr, trig;
+  int trig_n = 0;
+  float trig_min = 0.f, trig_inc = 0.f;
   DevBuf state[2], susp[2];                  /* suspended-pair state slots + pair lists, ping-pong between stages */
   unsigned long long *d_queue = nullptr;     /* [0..4] stage queue heads, [6],[7] suspended counts, [8..15] counters, [16..23] development phase timers */
   DevBuf gather;                             /* this rank's copy of the whole batch's records (fused gather)  */
@@ -173,6 +175,8 @@ int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t m
 template <bool PRUNED>
 int launch_icp_w(dpgicp_ctx *ctx, int nw, int csize, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
   nw = std::max(1, std::min(nw, 16));
+  /* first stage of large scans: 12 warps with the 80-register budget so that two CTAs share an SM */
+  if (csize == 1 && !kp.resume && nw > 8 && nw <= 12) return launch_icp_t<12, PRUNED, 1>(ctx, kp, smem, n, nw, grid_out);
   if (csize == 2) return launch_icp_t<16, PRUNED, 2>(ctx, kp, smem, n, nw, grid_out);
   if (csize == 4) return launch_icp_t<16, PRUNED, 4>(ctx, kp, smem, n, nw, grid_out);
   if (nw <= 1) return launch_icp_t<1, PRUNED, 1>(ctx, kp, smem, n, 1, grid_out);
@@ -241,11 +245,11 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
    * still running when a stage's queue runs dry; each width is balanced against the tile count */
   const int tiles = n_cap / kTile;
   int w0 = ctx->force_warps;
-  if (w0 <= 0) w0 = n_cap <= 512 ? 2 : (n_cap <= 2048 ? 4 : 8);
+  if (w0 <= 0) w0 = n_cap <= 512 ? 2 : (n_cap <= 2048 ? 4 : 12);
   struct StageShape { int warps, csize; };
   /* 34 tiles (1081 beams) -> 4, 7, 12 warps per CTA, then clusters of 4 CTAs x 9 warps (one tile per warp on four
    * SMs) for the last pairs: measured per-pass latency of one pair 28.7 / 17.9 / 11.4 / 6.3 us */
-  StageShape targets[5] = {{w0, 1}, {2 * w0, 1}, {16, 1}, {16, 4}, {16, 1}};
+  StageShape targets[5] = {{w0, 1}, {std::min(16, 2 * w0), 1}, {16, 1}, {16, 4}, {16, 1}};
   int n_targets = tiles >= 16 ? 4 : 3;
   if (!ctx->chain.empty()) {
     n_targets = 0;
@@ -390,6 +394,25 @@ int set_pairs_into(dpgicp_ctx *ctx, const Store &st, Batch &b, const int32_t *sr
   return DPGICP_OK;
 }
 
+/* cos/sin of every beam direction angle_i = angle_inc * i + angle_min (binary32, as createNode computes it,
+ * dpg_slam.cc:497-504), evaluated in binary64 by the host's libm like the reference's double overloads
+ * (dpg_measurement.h:102-104); uploaded once per scanner geometry */
+int ensure_trig(dpgicp_ctx *ctx, int n_beams, float angle_min, float angle_inc) {
+  if (ctx->trig_n == n_beams && ctx->trig_min == angle_min && ctx->trig_inc == angle_inc && ctx->trig.p) return DPGICP_OK;
+  std::vector<double> t((size_t)n_beams * 2);
+  for (int i = 0; i < n_beams; ++i) {
+    const float angle = angle_inc * (float)i + angle_min;
+    t[2 * (size_t)i] = std::cos((double)angle);
+    t[2 * (size_t)i + 1] = std::sin((double)angle);
+  }
+  int rc;
+  if ((rc = reserve(ctx, ctx->trig, sizeof(double) * t.size()))) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->trig.p, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));      /* t goes out of scope */
+  ctx->trig_n = n_beams; ctx->trig_min = angle_min; ctx->trig_inc = angle_inc;
+  return DPGICP_OK;
+}
+
 /* close the peer mappings of the fused gather */
 int gather_close(dpgicp_ctx *ctx) {
   for (int g = 0; g < ctx->gather_world; ++g) {
@@ -506,7 +529,7 @@ void dpgicp_destroy(dpgicp_ctx *ctx) {
   }
   gather_close(ctx);
   release(ctx->gather);
-  release(ctx->stage); release(ctx->offsets); release(ctx->misc); release(ctx->corr);
+  release(ctx->stage); release(ctx->offsets); release(ctx->misc); release(ctx->corr); release(ctx->trig);
   for (int k = 0; k < 2; ++k) { release(ctx->state[k]); release(ctx->susp[k]); }
   if (ctx->d_queue) cudaFree(ctx->d_queue);
   if (ctx->d_bad) cudaFree(ctx->d_bad);
@@ -570,8 +593,9 @@ int dpgicp_upload_ranges(dpgicp_ctx *ctx, const float *ranges, int32_t n_scans, 
   const float lc = cosf(ltheta), ls = sinf(ltheta);       /* Eigen::Rotation2Df(ltheta), host libm */
   const int threads = 128, warps_per_block = threads / 32;
   const int blocks = (n_scans + warps_per_block - 1) / warps_per_block;
-  ranges_to_rows_kernel<<<blocks, threads, 0, ctx->stream>>>((const float *)ctx->stage.p, nullptr, n_scans, n_beams, angle_min,
-                                                            angle_inc, range_max, lx, ly, lc, ls, pitch,
+  if ((rc = ensure_trig(ctx, n_beams, angle_min, angle_inc))) return rc;
+  ranges_to_rows_kernel<<<blocks, threads, 0, ctx->stream>>>((const float *)ctx->stage.p, nullptr, n_scans, n_beams,
+                                                            (const double2 *)ctx->trig.p, range_max, lx, ly, lc, ls, pitch,
                                                             (float2 *)st.rows.p, (int32_t *)st.count.p, ctx->d_bad);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
@@ -631,8 +655,9 @@ int dpgicp_upload_ranges_subset(dpgicp_ctx *ctx, const float *ranges, int32_t n_
   const float lc = cosf(ltheta), ls = sinf(ltheta);
   const int threads = 128, warps_per_block = threads / 32;
   const int blocks = (n_ids + warps_per_block - 1) / warps_per_block;
-  ranges_to_rows_kernel<<<blocks, threads, 0, ctx->stream>>>(d_in, d_ids, n_ids, n_beams, angle_min, angle_inc, range_max, lx, ly,
-                                                            lc, ls, pitch, (float2 *)st.rows.p, (int32_t *)st.count.p, ctx->d_bad);
+  if ((rc = ensure_trig(ctx, n_beams, angle_min, angle_inc))) return rc;
+  ranges_to_rows_kernel<<<blocks, threads, 0, ctx->stream>>>(d_in, d_ids, n_ids, n_beams, (const double2 *)ctx->trig.p, range_max,
+                                                            lx, ly, lc, ls, pitch, (float2 *)st.rows.p, (int32_t *)st.count.p, ctx->d_bad);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   return finish_store(ctx, st, n_ids);

@@ -1118,9 +1118,12 @@ __global__ void pack_rows_kernel(const unsigned char *__restrict__ pts, size_t s
 
 /* raw ranges -> base_link points, MAX_RANGE dropped, beam order kept (createNode
  * dpg_slam.cc:497-506, dpg_measurement.h:41-46,102-104, dpg_node.cc:13-22).  One warp per scan,
- * ballot-prefix compaction.  Trig in binary64 rounded to binary32, like the oracle. */
+ * ballot-prefix compaction.  The beam directions are the same for every scan, so cos/sin of
+ * angle_i = angle_inc * i + angle_min come from a table the host computed once with its own libm in
+ * binary64 — bit for bit what the oracle (and the reference's double overloads) use, and the kernel
+ * is left with a multiply per coordinate: HBM-bound, 4 B in + 8 B out per beam. */
 __global__ void ranges_to_rows_kernel(const float *__restrict__ ranges, const int32_t *__restrict__ scan_ids, int n_scans,
-                                      int n_beams, float angle_min, float angle_inc, float range_max, float lx, float ly,
+                                      int n_beams, const double2 *__restrict__ trig, float range_max, float lx, float ly,
                                       float lc, float ls, int pitch, float2 *rows, int32_t *count, int *bad) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n_scans) return;
@@ -1129,23 +1132,32 @@ __global__ void ranges_to_rows_kernel(const float *__restrict__ ranges, const in
   const float *r = ranges + (size_t)(scan_ids ? scan_ids[warp] : warp) * n_beams;
   float2 *row = rows + (size_t)warp * pitch;
   int n = 0;
-  for (int base = 0; base < n_beams; base += 32) {
-    const int i = base + lane;
-    float rg = range_max;
-    if (i < n_beams) rg = __ldg(r + i);
-    const bool keep = (i < n_beams) && !(rg >= range_max);
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      const float angle = __fadd_rn(__fmul_rn(angle_inc, (float)i), angle_min);
-      const float px = (float)__dmul_rn((double)rg, cos((double)angle));
-      const float py = (float)__dmul_rn((double)rg, sin((double)angle));
-      const float rx = __fadd_rn(__fmul_rn(lc, px), __fmul_rn(-ls, py));
-      const float ry = __fadd_rn(__fmul_rn(ls, px), __fmul_rn(lc, py));
-      const float2 v = make_float2(__fadd_rn(lx, rx), __fadd_rn(ly, ry));
-      if (!(fabsf(v.x) <= DPGICP_MAX_ABS_COORD) || !(fabsf(v.y) <= DPGICP_MAX_ABS_COORD)) atomicExch(bad, 1);
-      row[n + __popc(bal & ((1u << lane) - 1u))] = v;
+  for (int base = 0; base < n_beams; base += 128) {
+    /* four coalesced loads (and their table entries) in flight before the first dependent compaction step */
+    float rg[4];
+    double2 cs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + 32 * u + lane;
+      rg[u] = range_max;
+      cs[u] = make_double2(0.0, 0.0);
+      if (i < n_beams) { rg[u] = __ldg(r + i); cs[u] = __ldg(trig + i); }
     }
-    n += __popc(bal);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool keep = !(rg[u] >= range_max);          /* out-of-range lanes hold range_max */
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const float px = (float)__dmul_rn((double)rg[u], cs[u].x);
+        const float py = (float)__dmul_rn((double)rg[u], cs[u].y);
+        const float rx = __fadd_rn(__fmul_rn(lc, px), __fmul_rn(-ls, py));
+        const float ry = __fadd_rn(__fmul_rn(ls, px), __fmul_rn(lc, py));
+        const float2 v = make_float2(__fadd_rn(lx, rx), __fadd_rn(ly, ry));
+        if (!(fabsf(v.x) <= DPGICP_MAX_ABS_COORD) || !(fabsf(v.y) <= DPGICP_MAX_ABS_COORD)) atomicExch(bad, 1);
+        row[n + __popc(bal & ((1u << lane) - 1u))] = v;
+      }
+      n += __popc(bal);
+    }
   }
   for (int k = n + lane; k < pitch; k += 32) row[k] = make_float2(0.f, 0.f);
   if (lane == 0) count[warp] = n;
