@@ -108,6 +108,8 @@ int check_params(dpgicp_ctx *ctx, const dpgicp_params *p) {
   if (p->downsample_divisor < 1) return fail(ctx, DPGICP_E_INVALID, "downsample_divisor must be >= 1");
   if (!(p->max_correspondence_distance > 0.0) || !std::isfinite(p->max_correspondence_distance))
     return fail(ctx, DPGICP_E_INVALID, "max_correspondence_distance must be positive and finite");
+  if (p->max_correspondence_distance > 30.0)      /* sum of d^2 * 2^40 over 8192 pairs must fit int64 (arithmetic contract) */
+    return fail(ctx, DPGICP_E_INVALID, "max_correspondence_distance must be <= 30 m");
   if (!(p->transformation_epsilon >= 0.0)) return fail(ctx, DPGICP_E_INVALID, "transformation_epsilon must be >= 0");
   if (p->metric != DPGICP_METRIC_POINT_TO_POINT && p->metric != DPGICP_METRIC_POINT_TO_LINE)
     return fail(ctx, DPGICP_E_INVALID, "metric must be DPGICP_METRIC_POINT_TO_POINT or DPGICP_METRIC_POINT_TO_LINE");

@@ -86,7 +86,7 @@ typedef struct dpgicp_params {
   int32_t cov_mode;                    /* DPGICP_COV_*     (default REFERENCE_LIVE = drop-in)    */
   int32_t cov_cap;                     /* 200    cov_func_point_to_point.h:307; 0 = no cap       */
   double  transformation_epsilon;      /* 5e-9   parameters.h:159 */
-  double  max_correspondence_distance; /* 0.6    parameters.h:173 */
+  double  max_correspondence_distance; /* 0.6    parameters.h:173; must be <= 30 m (fixed-point sums) */
   double  cov_sensor_variance;         /* 0.01   cov_func_point_to_point.h:554 (cov_z = 0.01 I)  */
   float   laser_x_variance;            /* 0.5    parameters.h:374 */
   float   laser_y_variance;            /* 0.5    parameters.h:385 */

@@ -301,6 +301,64 @@ def test_error_codes(gpu_matcher):
     assert e.value.code == -6
 
 
+def test_random_small_problems_bit_exact(gpu_matcher):
+    """Many tiny random problems: 0..150 points per cloud, duplicated points and lattice ties, random gates, both
+    metrics, reciprocal on/off, all covariance modes, divisors 1..4, extreme coordinates (|x| up to 990 m)."""
+    rng = np.random.default_rng(2025)
+    clouds, offsets, family = [], [0], []
+    for base_id in range(40):
+        n = int(rng.choice([0, 1, 2, 3, 5, 17, 31, 32, 33, 64, 100, 150]))
+        centre = rng.uniform(-950, 950, 2) if base_id % 7 == 0 else rng.uniform(-20, 20, 2)
+        kind = base_id % 4
+        if kind == 0:      # wall-like polyline
+            t = np.sort(rng.uniform(0, 6, n))
+            pts = np.stack([t, 0.3 * np.sin(t)], 1)
+        elif kind == 1:    # lattice: exact distance ties
+            pts = np.stack([rng.integers(0, 8, n) * 0.25, rng.integers(0, 8, n) * 0.25], 1).astype(float)
+        elif kind == 2:    # duplicated points
+            base = rng.uniform(0, 3, (max(n // 2, 1), 2))
+            pts = base[rng.integers(0, len(base), n)] if n else np.zeros((0, 2))
+        else:
+            pts = rng.uniform(0, 4, (n, 2))
+        for variant in range(3):       # the base and two moved, noisy, thinned copies of it
+            v = pts.copy()
+            if variant:
+                th = rng.normal(0, 0.05)
+                R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+                v = v @ R.T + rng.normal(0, 0.1, 2)
+                if kind != 1:
+                    v = v + rng.normal(0, 0.005, v.shape)
+                v = v[rng.random(len(v)) < 0.9]
+            clouds.append((v + centre).astype(np.float32))
+            offsets.append(offsets[-1] + len(v))
+            family.append(base_id)
+    n_scans = len(clouds)
+    pts = np.concatenate(clouds).astype(np.float32)
+    off = np.array(offsets, np.int64)
+    gpu_matcher.upload_scans(pts, off)
+    n_pairs = 400
+    src = rng.integers(0, n_scans, n_pairs).astype(np.int32)
+    tgt = (3 * (src // 3) + rng.integers(0, 3, n_pairs)).astype(np.int32)          # same family (possibly itself)
+    far = rng.random(n_pairs) < 0.1
+    tgt[far] = rng.integers(0, n_scans, int(far.sum()))                             # some unrelated pairs
+    guess = np.zeros((n_pairs, 3), np.float32)
+    guess[:, :2] = rng.normal(0, 0.08, (n_pairs, 2))
+    guess[:, 2] = rng.normal(0, 0.04, n_pairs)
+    for trial in range(10):
+        p = Params.defaults(downsample_divisor=int(rng.integers(1, 5)), cov_mode=int(rng.integers(0, 3)),
+                            metric=int(rng.integers(0, 2)), use_reciprocal=int(rng.integers(0, 2)),
+                            search=int(rng.integers(0, 2)), max_iterations=int(rng.choice([1, 3, 25, 500])),
+                            max_correspondence_distance=float(rng.choice([0.05, 0.6, 2.5])),
+                            cov_cap=int(rng.choice([0, 5, 200])))
+        got = gpu_matcher.submit_pairs(src, tgt, guess, p)
+        ref, _ = O.run_batch(pts, off, src, tgt, guess, p, fast=int(rng.integers(0, 2)), threads=0)
+        assert_records_match(got, ref, f"random trial {trial}: div {p.downsample_divisor} cov {p.cov_mode} metric {p.metric} "
+                                       f"rec {p.use_reciprocal} search {p.search} it {p.max_iterations} gate {p.max_correspondence_distance}")
+    with pytest.raises(DpgIcpError) as e:
+        gpu_matcher.submit_pairs(src[:1], tgt[:1], guess[:1], Params.defaults(max_correspondence_distance=31.0))
+    assert e.value.code == -1
+
+
 # ---- the two reference call shapes -------------------------------------------------------------------------------
 def test_run_icp_call_shape(gpu_matcher):
     wl = synth.config_room_pair()
