@@ -82,7 +82,7 @@ def workload_config(n_gpus: int, extra=None):
            "fov_deg": 270, "downsample_divisor": 1, "metric_kind": "point_to_line" if w["metric"] else "point_to_point",
            "reciprocal": True,
            "cov_mode": "CENSI_CORR(cap 200)", "max_iterations": 500, "max_correspondence_distance_m": 0.6,
-           "search": "exact pruned (bounding-box groups)", "sharding": f"round-robin over {n_gpus} GPU(s), scan store replicated, records gathered by peer stores from the kernel epilogue",
+           "search": "exact pruned (bounding-box groups)", "sharding": f"round-robin over {n_gpus} GPU(s), scan store replicated",
            "l2": "flushed between timed steps (512 MiB memset outside the event pair)", "seed": w["seed"]}
     if extra:
         cfg.update(extra)
@@ -246,7 +246,7 @@ def run_product(args):
         # whole-batch buffer over NVLink); DPGICP_BENCH_GATHER=nccl uses an all-gather collective after the kernel
         fused = world > 1 and os.environ.get("DPGICP_BENCH_GATHER", "fused") != "nccl"
         if fused:
-            shard.attach_fused_gather(n_global)
+            fused = shard.attach_fused_gather(n_global)       # False on every rank if a peer buffer could not be mapped
 
         def step_resident():
             shard.run(p)
@@ -404,7 +404,9 @@ def run_product(args):
     conv = float(((rec_local["status"] & FLAG_CONVERGED) != 0).mean())
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world, {"gather": "none (1 GPU)" if world == 1 else
+                                              ("peer stores from the kernel epilogue (fused)" if fused else "NCCL all_gather")}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "timing": "host clock around upload+convert+pairs+ICP/cov+fetch, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -155,16 +155,37 @@ class ShardedScanMatcher:
         return self._recv
 
     # ---- gather fused into the kernel: no collective on the data path ----------------------------------------
-    def attach_fused_gather(self, n_global_pairs: int):
+    def attach_fused_gather(self, n_global_pairs: int) -> bool:
         """Exchange CUDA IPC handles of per-rank whole-batch buffers once; afterwards every ``run`` writes its
-        records straight into all ranks' buffers from the kernel epilogue (peer stores over NVLink)."""
+        records straight into all ranks' buffers from the kernel epilogue (peer stores over NVLink).  Returns
+        False — on EVERY rank, after an agreement round — when some rank could not map a peer's buffer (no
+        peer access between the devices); the caller then gathers with :meth:`gather_device` (NCCL)."""
+        import torch
         import torch.distributed as dist
-        mine = self.sm.gather_export(n_global_pairs)
+        ok = 1
+        try:
+            mine = self.sm.gather_export(n_global_pairs)
+        except Exception:
+            mine, ok = b"\0" * 64, 0
         handles = [None] * self.world
         dist.all_gather_object(handles, mine, group=self.group)
-        self.sm.gather_attach(handles, self.rank)
+        if ok:
+            try:
+                self.sm.gather_attach(handles, self.rank)
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            try:
+                self.sm.gather_detach()
+            except Exception:
+                pass
+            self._fused = 0
+            return False
         self._fused = int(n_global_pairs)
         dist.barrier(group=self.group)
+        return True
 
     def detach_fused_gather(self):
         import torch.distributed as dist
