@@ -16,13 +16,19 @@
  * (d2, index)-lexicographic nearest neighbour, exact int64 fixed-point moment sums (order
  * independent, so any thread layout gives the same bits), binary64 closed-form planar step.
  *
- * Exact pruned search: points of a scan are in beam order, so 32 consecutive points form a
- * spatially compact group with an axis-aligned bounding box.  A warp handles 32 consecutive
+ * Exact pruned search: points of a scan are in beam order, so kGroup (16) consecutive points form a
+ * spatially compact group with an axis-aligned bounding box.  A warp handles a tile of 32 consecutive
  * queries (one per lane); box-to-box lower bounds (evaluated lane-parallel over groups) select
  * the groups that can still beat the tile's current bound, which is seeded with the previous
  * iteration's neighbour.  Lower bounds use the same rounding sequence as the distance itself, so
  * by monotonicity of rounding they never exceed a computed distance: pruning is exact, no
  * epsilons.  SEARCH_BRUTE scans every group through the same code.
+ *
+ * Execution shapes: the host launches the kernel as a chain of stages with
+ * growing warps per pair; a stage suspends the pairs still running when its queue runs dry (state to
+ * HBM, restored bit for bit) and the last stage gives each remaining pair a thread-block cluster of
+ * 4 CTAs that exchange exact partial sums through distributed shared memory.  With a multi-GPU
+ * gather attached, the epilogue stores each record into every rank's buffer over NVLink.
  */
 #pragma once
 
