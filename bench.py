@@ -397,7 +397,10 @@ def run_product(args):
         dt, used, cref = cpu_sample_run(wl, pts, off, p, cidx)
         same = all(np.array_equal(cref[f], rec_local[cidx][f]) for f in
                    ("tx", "ty", "iterations", "status", "n_correspondences", "mse"))
+        sidx = cidx[::max(1, len(cidx) // 48)][:48]             # the reference itself is single-threaded (ros::spin)
+        dt1, _, _ = cpu_sample_run(wl, pts, off, p, sidx, threads=1)
         cpu = {"value": len(cidx) / dt, "unit": UNIT, "cores": used, "kind": "port",
+               "single_thread_value": len(sidx) / dt1, "single_thread_sample": f"{len(sidx)} pairs, {dt1:.1f} s",
                "sample": f"{len(cidx)} of {wl.n_pairs} pairs (evenly strided), {dt:.1f} s, oracle port with exact uniform-grid NN, "
                          f"OpenMP over pairs", "records_equal_gpu": bool(same)}
 
@@ -411,7 +414,8 @@ def run_product(args):
                     "steps": e2e_steps, "timing": "host clock around upload+convert+pairs+ICP/cov+fetch, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "wall_s_timed_region": t_wall,
-            "stats": {"mean_iterations": float(rec_local["iterations"].mean()), "max_iterations": int(rec_local["iterations"].max()),
+            "stats": {"mean_iterations": float(rec_local["iterations"].mean()), "p95_iterations": float(np.percentile(rec_local["iterations"], 95)),
+                      "max_iterations": int(rec_local["iterations"].max()),
                       "converged_frac": conv, "distance_evals_per_launch": counters["distance_evals"],
                       "box_tests_per_launch": counters["box_tests"]}}
     print(json.dumps(line), flush=True)
