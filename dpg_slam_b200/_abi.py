@@ -156,6 +156,7 @@ def load_library() -> C.CDLL:
         "dpgicp_last_run_counters": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
         "dpgicp_single_pair": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, PR]),
         "dpgicp_cov": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, vp, C.POINTER(C.c_uint32)]),
+        "dpgicp_cov_pairs": (C.c_int, [vp, vp, vp, vp, i64, PP, vp, vp, C.POINTER(C.c_float)]),
         "dpgicp_correspondences": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, vp, vp]),
         "dpgicp_relative_guess": (C.c_int, [vp, vp, vp]),
         "dpgicp_fp32_probe": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -1075,14 +1075,24 @@ __global__ void __launch_bounds__(WARPS * 32) cov_indexpair_kernel(const CovItem
 #pragma unroll
   for (int k = 0; k < 11; ++k) acc[k] = 0.0;
   if (cov_mode != DPGICP_COV_REFERENCE_LIVE) {
+    /* pose as cov.h:26-35; the trigonometry once per CTA, broadcast through shared memory */
+    if (threadIdx.x == 0) {
+      const double a = (double)atan2f(it.s, it.c);
+      dpart[0] = cos(a); dpart[1] = sin(a);
+    }
+    __syncthreads();
     const double x = (double)it.tx, y = (double)it.ty;
-    const double a = (double)atan2f(it.s, it.c);
-    const double ca = cos(a), sa = sin(a);
+    const double ca = dpart[0], sa = dpart[1];
+    __syncthreads();                                   /* dpart is reused by the reduction below */
     const int nh = it.n_p < it.n_q ? it.n_p : it.n_q;
     const int nd = (cov_cap > 0 && nh > cov_cap) ? cov_cap : nh;
-    for (int k = threadIdx.x; k < nh; k += WARPS * 32) {
-      const float2 p = __ldg(it.p + k), q = __ldg(it.q + k);
+    /* two index pairs per 16-byte load (rows are 16-byte aligned): 32 bytes in flight per thread and trip */
+    const float4 *p4 = reinterpret_cast<const float4 *>(it.p), *q4 = reinterpret_cast<const float4 *>(it.q);
+    for (int k2 = threadIdx.x; 2 * k2 < nh; k2 += WARPS * 32) {
+      const float4 p = __ldg(p4 + k2), q = __ldg(q4 + k2);
+      const int k = 2 * k2;
       cov_terms(p.x, p.y, q.x, q.y, ca, sa, x, y, true, k < nd, acc);
+      if (k + 1 < nh) cov_terms(p.z, p.w, q.z, q.w, ca, sa, x, y, true, k + 1 < nd, acc);
     }
   }
   block_sum11<WARPS>(acc, dpart, S);

@@ -255,6 +255,20 @@ class ScanMatcher:
                                          Tc.ctypes.data, C.byref(p), cov.ctypes.data, C.byref(st)))
         return cov.reshape(3, 3), int(st.value)
 
+    def calculate_icp_cov_pairs(self, data_idx, model_idx, T, params: Optional[Params] = None):
+        """Batched ``calculate_ICP_COV`` over the scan store: item k pairs scans ``data_idx[k]`` / ``model_idx[k]`` by
+        index under ``T[k] = (T00, T10, T03, T13)``.  Returns ``(cov (n, 3, 3), status (n,), kernel_ms)``."""
+        p = params or Params.defaults()
+        a = np.ascontiguousarray(data_idx, np.int32)
+        b = np.ascontiguousarray(model_idx, np.int32)
+        t = np.ascontiguousarray(T, np.float32).reshape(-1, 4)
+        cov = np.zeros((a.shape[0], 9), np.float64)
+        st = np.zeros(a.shape[0], np.uint32)
+        ms = C.c_float(0)
+        self._check(self._lib.dpgicp_cov_pairs(self._h, a.ctypes.data, b.ctypes.data, t.ctypes.data, a.shape[0], C.byref(p),
+                                               cov.ctypes.data, st.ctypes.data, C.byref(ms)))
+        return cov.reshape(-1, 3, 3), st, float(ms.value)
+
     # ---- parity hook + callers' gate ---------------------------------------------------------------------
     def correspondences(self, source_ds, target_ds, T, params: Params):
         """One correspondence pass at iterate T = (c, s, tx, ty) -> (corr_tgt int32, d2 float32)."""

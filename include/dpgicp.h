@@ -214,6 +214,14 @@ int  dpgicp_cov(dpgicp_ctx *ctx,
                 size_t stride_bytes, const float transform_colmajor[16],
                 const dpgicp_params *params, double cov_out[9], uint32_t *status_out);
 
+/* Batched form over the scan store: item k is calculate_ICP_COV(data_pi = scan data_idx[k], model_qi = scan
+ * model_idx[k], T[k]) with T[k] = (T(0,0), T(1,0), T(0,3), T(1,3)) of the 4x4 transform; cov_out = 9 doubles and
+ * status_out = one word per item.  One CTA per item; HBM-bound (16 bytes read per index pair).  kernel_ms (may be
+ * NULL) receives the device time of the kernel alone (CUDA events on the context's stream).                 */
+int  dpgicp_cov_pairs(dpgicp_ctx *ctx, const int32_t *data_idx, const int32_t *model_idx, const float *T,
+                      int64_t n_items, const dpgicp_params *params, double *cov_out, uint32_t *status_out,
+                      float *kernel_ms);
+
 /* Host helper, no device work: the guess runIcp derives from two node pose estimates
  * (dpg_slam.cc:364-370 = math_utils::inverseTransformPoint, math_utils.cc:20-34, and AngleMod,
  * math_utils.h:13-16), in the reference's float arithmetic.  pose = (x, y, theta).             */

@@ -390,6 +390,33 @@ def test_calculate_icp_cov_against_compiled_reference(gpu_matcher, cov_golden):
         assert rel < 1e-7, (c["name"], rel)                                       # in practice: double rounding only (n = 3 is ill-conditioned)
 
 
+def test_batched_covariance_over_the_store(gpu_matcher):
+    """dpgicp_cov_pairs == the oracle's index-paired Censi form per item (and == the single-item call)."""
+    wl = synth.config_corridor(n_pairs=50, n_beams=721, seed=27)
+    wl.ranges[3, ::3] = 40.0                                        # clouds of different lengths
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    pts, off = gpu_matcher.download_store()
+    rng = np.random.default_rng(5)
+    th = rng.normal(0, 0.05, 50).astype(np.float32)
+    T = np.stack([np.cos(th.astype(np.float64)).astype(np.float32), np.sin(th.astype(np.float64)).astype(np.float32),
+                  wl.truth[:, 0].astype(np.float32), wl.truth[:, 1].astype(np.float32)], 1)
+    p = Params.defaults(cov_mode=COV_CENSI_INDEXPAIR)
+    cov, st, ms = gpu_matcher.calculate_icp_cov_pairs(wl.src_idx, wl.tgt_idx, T, p)
+    assert ms > 0 and cov.shape == (50, 3, 3)
+    for k in range(50):
+        P = pts[off[wl.src_idx[k]]:off[wl.src_idx[k] + 1]]
+        Q = pts[off[wl.tgt_idx[k]]:off[wl.tgt_idx[k] + 1]]
+        nh = min(len(P), len(Q))
+        s_ref, want, _ = O.cov_censi(P, Q, nh, min(nh, 200), T[k])
+        assert st[k] == s_ref
+        rel = np.abs(cov[k] - want).max() / np.abs(want).max()
+        assert rel <= COV_REL_TOL and rel < 1e-7, (k, rel)
+    live, st, _ = gpu_matcher.calculate_icp_cov_pairs(wl.src_idx, wl.tgt_idx, T, Params.defaults())
+    assert np.all(live == np.diag([0.5, 0.5, np.float64(np.float32(0.3))]))
+    with pytest.raises(DpgIcpError):
+        gpu_matcher.calculate_icp_cov_pairs([99], [0], T[:1], p)
+
+
 def test_enumerate_pairs_matches_oracle(gpu_matcher):
     rng = np.random.default_rng(17)
     for n in (0, 1, 2, 3, 200, 1500):
