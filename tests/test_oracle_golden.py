@@ -281,3 +281,53 @@ def test_factor_sqrt_information():
     assert np.allclose(f["sqrt_info"][1].reshape(3, 3), np.diag([2 ** 0.5, 2 ** 0.5, (1 / 0.3) ** 0.5]))
     assert f["status"][2] & FLAG_FACTOR_INVALID and not f["sqrt_info"][2].any()
     assert list(f["from_node"]) == [0, 1, 2] and list(f["to_node"]) == [1, 2, 3] and f["tx"][1] == 2
+
+
+# ---- rigid step vs Eigen's published Umeyama algorithm in float32 3-D (what PCL's TransformationEstimationSVD runs) ----
+def _umeyama_float32_3d(P, Q):
+    """Eigen::umeyama(src, dst, with_scaling=false) restated (Geometry/Umeyama.h): float32, 3-D points with z = 0."""
+    f = np.float32
+    src = np.concatenate([P, np.zeros((len(P), 1))], 1).astype(f).T       # 3 x n
+    dst = np.concatenate([Q, np.zeros((len(Q), 1))], 1).astype(f).T
+    n = f(src.shape[1])
+    mu_s = (src.sum(1) / n).astype(f)
+    mu_d = (dst.sum(1) / n).astype(f)
+    sd, dd = (src - mu_s[:, None]).astype(f), (dst - mu_d[:, None]).astype(f)
+    sigma = ((dd @ sd.T) / n).astype(f)
+    U, d, Vt = np.linalg.svd(sigma.astype(f))
+    S = np.ones(3, f)
+    if np.linalg.det(U.astype(np.float64)) * np.linalg.det(Vt.astype(np.float64)) < 0:
+        S[2] = -1
+    R = (U * S) @ Vt
+    t = mu_d - R @ mu_s
+    return R.astype(f), t.astype(f)
+
+
+def test_planar_closed_form_equals_float32_umeyama_svd():
+    """The oracle's binary64 planar Procrustes step is the z = 0 case of PCL's float SVD step: they agree to the
+    float32 noise of the SVD path (SURVEY.md A.6 measured <= 1.4e-6 m / 4e-8 rad), far inside the 1e-5 bar."""
+    wl = synth.config_loop_closure(n_pairs=10, n_scans=30, seed=9)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    p = Params.defaults(downsample_divisor=1, max_iterations=1)
+    worst_t, worst_r = 0.0, 0.0
+    for k in range(wl.n_pairs):
+        s, t = wl.src_idx[k], wl.tgt_idx[k]
+        src, tgt = pts[off[s]:off[s + 1]], pts[off[t]:off[t + 1]]
+        res = O.icp(src, tgt, wl.guess[k], p)
+        if res.n_correspondences < 3:
+            continue
+        G = O.guess_matrix(wl.guess[k])
+        cur = O.transform_points(G, src)
+        _, corr, _ = O.correspondences(cur, tgt, p)
+        m = corr >= 0
+        R, tt = _umeyama_float32_3d(cur[m], tgt[corr[m]])
+        assert abs(R[2, 2] - 1.0) < 1e-6 and abs(tt[2]) < 1e-6          # stays planar (dpg_slam.cc:418-426 checks this)
+        # final = step * guess, as the Matrix4f product
+        c, sn = np.float64(G[0]), np.float64(G[1])
+        Rg = np.array([[c, -sn], [sn, c]])
+        Rf = R[:2, :2].astype(np.float64) @ Rg
+        tf = R[:2, :2].astype(np.float64) @ np.array([G[2], G[3]], np.float64) + tt[:2]
+        th = np.arctan2(Rf[1, 0], Rf[0, 0])
+        worst_t = max(worst_t, abs(tf[0] - res.tx), abs(tf[1] - res.ty))
+        worst_r = max(worst_r, abs(th - res.theta))
+    assert worst_t < 5e-6 and worst_r < 2e-6, (worst_t, worst_r)
