@@ -370,9 +370,12 @@ int set_pairs_into(dpgicp_ctx *ctx, const Store &st, Batch &b, const int32_t *sr
     CU_TRY(ctx, cudaMallocHost((void **)&b.h_tasks, sizeof(PairTask) * (size_t)n));
     b.h_tasks_cap = (size_t)n;
   }
+  /* host threads share the loop (the libm cos/sin of the guesses is the bulk of it); the first offending pair is
+   * reported, as the serial loop would */
+  int64_t bad_index = n, bad_guess = n;
+#pragma omp parallel for schedule(static) reduction(min : bad_index, bad_guess) if (n >= 4096)
   for (int64_t k = 0; k < n; ++k) {
-    if (src[k] < 0 || src[k] >= st.n_scans || tgt[k] < 0 || tgt[k] >= st.n_scans)
-      return fail(ctx, DPGICP_E_INVALID, "pair index out of range at pair " + std::to_string(k));
+    if (src[k] < 0 || src[k] >= st.n_scans || tgt[k] < 0 || tgt[k] >= st.n_scans) { if (k < bad_index) bad_index = k; continue; }
     PairTask t;
     t.src = src[k]; t.tgt = tgt[k];
     if (T_direct) {
@@ -381,12 +384,14 @@ int set_pairs_into(dpgicp_ctx *ctx, const Store &st, Batch &b, const int32_t *sr
       /* Matrix4f guess of runIcp (dpg_slam.cc:374-378): cos/sin of the float angle, binary64 libm
        * rounded to binary32 (computed on the host so device and CPU agree bit for bit) */
       const float g0 = guess[3 * k], g1 = guess[3 * k + 1], g2 = guess[3 * k + 2];
-      if (!std::isfinite(g0) || !std::isfinite(g1) || !std::isfinite(g2))
-        return fail(ctx, DPGICP_E_RANGE, "non-finite guess at pair " + std::to_string(k));
+      if (!std::isfinite(g0) || !std::isfinite(g1) || !std::isfinite(g2)) { if (k < bad_guess) bad_guess = k; continue; }
       t.c = (float)std::cos((double)g2); t.s = (float)std::sin((double)g2); t.tx = g0; t.ty = g1;
     }
     b.h_tasks[k] = t;
   }
+  if (bad_index < n && bad_index <= bad_guess)
+    return fail(ctx, DPGICP_E_INVALID, "pair index out of range at pair " + std::to_string(bad_index));
+  if (bad_guess < n) return fail(ctx, DPGICP_E_RANGE, "non-finite guess at pair " + std::to_string(bad_guess));
   int rc;
   if ((rc = reserve(ctx, b.tasks, sizeof(PairTask) * (size_t)std::max<int64_t>(n, 1)))) return rc;
   if ((rc = reserve(ctx, b.results, sizeof(dpgicp_result) * (size_t)std::max<int64_t>(n, 1)))) return rc;
