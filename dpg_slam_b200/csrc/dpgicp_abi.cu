@@ -6,6 +6,7 @@
  * behind these entry points (dpgicp_create fails without a CUDA device).
  */
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      /* header-only; ranges show the batch phases in Nsight timelines, no-ops otherwise */
 
 #include <algorithm>
 #include <cmath>
@@ -22,6 +23,11 @@
 using namespace dpg;
 
 namespace {
+
+struct NvtxRange {                 /* scoped NVTX range */
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 std::string g_create_error;
 
@@ -204,6 +210,7 @@ int balanced_warps(int tiles, int target, int csize = 1) {
 
 int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_params *p, int32_t *corr_out,
                float *corr_d2) {
+  NvtxRange range("dpgicp: ICP + covariance stage chain");
   const int div = p->downsample_divisor;
   int n_max = (st.max_count + div - 1) / div;
   int n_cap = ((std::max(n_max, 1) + kTile - 1) / kTile) * kTile;
@@ -579,6 +586,7 @@ int dpgicp_upload_scans(dpgicp_ctx *ctx, const void *points, size_t stride, cons
 int dpgicp_upload_ranges(dpgicp_ctx *ctx, const float *ranges, int32_t n_scans, int32_t n_beams, float angle_min,
                          float angle_max, float range_max, float lx, float ly, float ltheta) {
   if (!ctx) return DPGICP_E_INVALID;
+  NvtxRange range("dpgicp: upload ranges + scan->cloud");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if (n_scans < 0 || n_beams < 2 || (n_scans > 0 && !ranges)) return fail(ctx, DPGICP_E_INVALID, "bad range-scan arguments");
   if (n_beams > DPGICP_MAX_POINTS) return fail(ctx, DPGICP_E_TOOBIG, "n_beams exceeds DPGICP_MAX_POINTS");
@@ -690,6 +698,7 @@ int dpgicp_download_scan(dpgicp_ctx *ctx, int32_t scan, float *xy, int32_t *n_po
 
 int dpgicp_set_pairs(dpgicp_ctx *ctx, const int32_t *src, const int32_t *tgt, const float *guess, int64_t n) {
   if (!ctx) return DPGICP_E_INVALID;
+  NvtxRange range("dpgicp: pair list");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   return set_pairs_into(ctx, ctx->store, ctx->batch, src, tgt, guess, nullptr, n);
 }
@@ -707,6 +716,7 @@ int dpgicp_run(dpgicp_ctx *ctx, const dpgicp_params *params) {
 
 int dpgicp_fetch_results(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n) {
   if (!ctx) return DPGICP_E_INVALID;
+  NvtxRange range("dpgicp: fetch records");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if (n < 0 || n > ctx->batch.n_pairs || (n > 0 && !out)) return fail(ctx, DPGICP_E_INVALID, "bad fetch arguments");
   if (n > 0)
