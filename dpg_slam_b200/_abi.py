@@ -102,7 +102,7 @@ EXPORTS = [
     "dpgicp_abi_version", "dpgicp_default_params", "dpgicp_create", "dpgicp_destroy",
     "dpgicp_last_error", "dpgicp_set_stream", "dpgicp_synchronize", "dpgicp_upload_scans",
     "dpgicp_upload_ranges", "dpgicp_upload_ranges_subset", "dpgicp_scan_count", "dpgicp_download_scan", "dpgicp_submit_pairs",
-    "dpgicp_set_pairs", "dpgicp_run", "dpgicp_fetch_results", "dpgicp_fetch_factors", "dpgicp_results_device_ptr",
+    "dpgicp_set_pairs", "dpgicp_set_pair_cost_hints", "dpgicp_run", "dpgicp_fetch_results", "dpgicp_fetch_factors", "dpgicp_results_device_ptr",
     "dpgicp_gather_export", "dpgicp_gather_attach", "dpgicp_gather_detach", "dpgicp_gather_fetch",
     "dpgicp_gather_device_ptr", "dpgicp_last_run_counters", "dpgicp_single_pair", "dpgicp_cov", "dpgicp_cov_pairs", "dpgicp_correspondences",
     "dpgicp_enumerate_pairs", "dpgicp_relative_guess", "dpgicp_fp32_probe",
@@ -144,6 +144,7 @@ def load_library() -> C.CDLL:
         "dpgicp_download_scan": (C.c_int, [vp, i32, vp, C.POINTER(i32)]),
         "dpgicp_submit_pairs": (C.c_int, [vp, vp, vp, vp, i64, PP, vp]),
         "dpgicp_set_pairs": (C.c_int, [vp, vp, vp, vp, i64]),
+        "dpgicp_set_pair_cost_hints": (C.c_int, [vp, vp, i64]),
         "dpgicp_run": (C.c_int, [vp, PP]),
         "dpgicp_fetch_results": (C.c_int, [vp, vp, i64]),
         "dpgicp_fetch_factors": (C.c_int, [vp, vp, i64]),

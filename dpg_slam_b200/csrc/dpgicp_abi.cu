@@ -43,7 +43,8 @@ struct Store {                 /* padded rows + counts on the device, counts mir
 };
 
 struct Batch {
-  DevBuf tasks, results;
+  DevBuf tasks, results, order;
+  bool has_order = false;
   PairTask *h_tasks = nullptr;   /* pinned */
   size_t h_tasks_cap = 0;
   int64_t n_pairs = 0;
@@ -222,6 +223,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   kp.store.pitch = st.pitch;
   kp.store.n_scans = st.n_scans;
   kp.tasks = (const PairTask *)b.tasks.p;
+  kp.order = b.has_order ? (const long long *)b.order.p : nullptr;
   kp.results = (dpgicp_result *)b.results.p;
   kp.counters = ctx->d_queue + 8;
   kp.n_pairs = b.n_pairs;
@@ -405,6 +407,7 @@ int set_pairs_into(dpgicp_ctx *ctx, const Store &st, Batch &b, const int32_t *sr
   if (n > 0)
     CU_TRY(ctx, cudaMemcpyAsync(b.tasks.p, b.h_tasks, sizeof(PairTask) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   b.n_pairs = n;
+  b.has_order = false;
   return DPGICP_OK;
 }
 
@@ -538,7 +541,7 @@ void dpgicp_destroy(dpgicp_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (Store *s : {&ctx->store, &ctx->scratch_store}) { release(s->rows); release(s->count); }
   for (Batch *b : {&ctx->batch, &ctx->scratch_batch}) {
-    release(b->tasks); release(b->results);
+    release(b->tasks); release(b->results); release(b->order);
     if (b->h_tasks) cudaFreeHost(b->h_tasks);
   }
   gather_close(ctx);
@@ -701,6 +704,33 @@ int dpgicp_set_pairs(dpgicp_ctx *ctx, const int32_t *src, const int32_t *tgt, co
   NvtxRange range("dpgicp: pair list");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   return set_pairs_into(ctx, ctx->store, ctx->batch, src, tgt, guess, nullptr, n);
+}
+
+int dpgicp_set_pair_cost_hints(dpgicp_ctx *ctx, const float *hints, int64_t n) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  Batch &b = ctx->batch;
+  if (!hints) { b.has_order = false; return DPGICP_OK; }
+  if (n != b.n_pairs) return fail(ctx, DPGICP_E_INVALID, "hint count differs from the pair list");
+  if (n == 0) return DPGICP_OK;
+  /* Only the quarter of the pairs with the largest hints is moved to the front (most expensive first); the rest keep
+   * their input order.  A full descending sort would put every pair predicted cheap at the very end — exactly where
+   * a mispredicted long alignment hurts most; this way a misprediction starts at an arbitrary time, as without
+   * hints, and scan locality of the input order is mostly kept. */
+  std::vector<long long> order((size_t)n);
+  for (int64_t k = 0; k < n; ++k) order[(size_t)k] = k;
+  const int64_t head = std::max<int64_t>(1, n / 4);
+  std::nth_element(order.begin(), order.begin() + (head - 1), order.end(),
+                   [&](long long a, long long c) { return hints[a] > hints[c] || (hints[a] == hints[c] && a < c); });
+  std::sort(order.begin(), order.begin() + head,
+            [&](long long a, long long c) { return hints[a] > hints[c] || (hints[a] == hints[c] && a < c); });
+  std::sort(order.begin() + head, order.end());
+  int rc;
+  if ((rc = reserve(ctx, b.order, sizeof(long long) * (size_t)n))) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(b.order.p, order.data(), sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));        /* `order` goes out of scope */
+  b.has_order = true;
+  return DPGICP_OK;
 }
 
 int dpgicp_run(dpgicp_ctx *ctx, const dpgicp_params *params) {

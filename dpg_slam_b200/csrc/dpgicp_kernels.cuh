@@ -94,6 +94,8 @@ struct KernelParams {
   float *corr_d2_out;
   /* staged execution (see icp_pairs_kernel): work items of stage > 0 are the pairs the previous
    * stage suspended when its queue ran dry; they are resumed by wider CTAs                        */
+  const long long *order;             /* fresh stage only: item k is pair order[k] (nullptr = identity): callers that
+                                       * know which pairs tend to run long put them first                         */
   int32_t resume;                     /* 0: items are fresh tasks; 1: items are susp_in[0..*in_count) */
   const unsigned int *in_count;
   const long long *susp_in;           /* pair index per suspended item; item k's state is slot k   */
@@ -617,7 +619,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
     pair_sync<CSIZE>();
     const unsigned long long item = ((unsigned long long)(uint32_t)L.ctl[1] << 32) | (uint32_t)L.ctl[0];
     if (item >= n_items) break;
-    const long long pair = P.resume ? P.susp_in[item] : (long long)item;
+    const long long pair = P.resume ? P.susp_in[item] : (P.order ? P.order[item] : (long long)item);
     const unsigned char *slot_in = P.resume ? P.state_in + (size_t)item * (size_t)P.slot_bytes : nullptr;
     const PairTask task = P.tasks[pair];
     const float2 *srow = P.store.pts + (size_t)task.src * P.store.pitch;

@@ -162,6 +162,15 @@ class ScanMatcher:
         self._n_pairs = s.shape[0]
         self._check(self._lib.dpgicp_set_pairs(self._h, s.ctypes.data, t.ctypes.data, g.ctypes.data, s.shape[0]))
 
+    def set_pair_cost_hints(self, hints):
+        """Expected relative cost per pair of the list set last (e.g. last time's ``iterations``): pairs are started
+        in descending order so that long alignments do not start last.  ``None`` clears it."""
+        if hints is None:
+            self._check(self._lib.dpgicp_set_pair_cost_hints(self._h, None, 0))
+            return
+        h = np.ascontiguousarray(hints, np.float32)
+        self._check(self._lib.dpgicp_set_pair_cost_hints(self._h, h.ctypes.data, h.shape[0]))
+
     def run(self, params: Params):
         """Launch the resident batch asynchronously on the context's stream."""
         self._check(self._lib.dpgicp_run(self._h, C.byref(params)))

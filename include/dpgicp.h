@@ -171,6 +171,11 @@ int  dpgicp_submit_pairs(dpgicp_ctx *ctx, const int32_t *src_idx, const int32_t 
 int  dpgicp_set_pairs(dpgicp_ctx *ctx, const int32_t *src_idx, const int32_t *tgt_idx,
                       const float *guess, int64_t n_pairs);            /* H2D of the pair list   */
 int  dpgicp_run(dpgicp_ctx *ctx, const dpgicp_params *params);         /* async on ctx stream    */
+/* Optional scheduling hint for the pair list set last: expected relative cost per pair (e.g. the iteration counts of
+ * the previous alignment of the same pairs — reoptimize(), dpg_slam.cc:35-120, re-aligns every pair after each pass).
+ * Pairs are then started in descending hint order, so long alignments do not start last.  Results do not depend on
+ * it (tested).  NULL clears the hint; set_pairs clears it too.                                                  */
+int  dpgicp_set_pair_cost_hints(dpgicp_ctx *ctx, const float *hints, int64_t n_pairs);
 int  dpgicp_fetch_results(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n_pairs); /* D2H + sync   */
 /* Records of the last dpgicp_run turned into pose-graph factors on the device (one per pair, pair order). */
 int  dpgicp_fetch_factors(dpgicp_ctx *ctx, dpgicp_factor *out, int64_t n_pairs);

@@ -570,6 +570,22 @@ def test_staged_chain_equals_single_stage(gpu_matcher, monkeypatch):
                     assert got.tobytes() == ref.tobytes(), (chain, cov_mode, metric, div)
 
 
+def test_cost_hints_change_the_schedule_not_the_results(gpu_matcher):
+    wl = synth.config_corridor(n_pairs=1200, seed=29)
+    p = Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR)
+    gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+    want = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+    gpu_matcher.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
+    for hints in (want["iterations"].astype(np.float32), -want["iterations"].astype(np.float32),
+                  np.random.default_rng(1).random(1200).astype(np.float32)):
+        gpu_matcher.set_pair_cost_hints(hints)
+        gpu_matcher.run(p)
+        assert gpu_matcher.fetch_results().tobytes() == want.tobytes()
+    gpu_matcher.set_pair_cost_hints(None)
+    with pytest.raises(DpgIcpError):
+        gpu_matcher.set_pair_cost_hints(np.zeros(5, np.float32))
+
+
 def test_rotation_entries_stay_orthonormal(gpu_matcher):
     wl = synth.config_loop_closure(n_pairs=2000, n_scans=400, seed=13)
     p = Params.defaults(downsample_divisor=5)
