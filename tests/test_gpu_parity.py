@@ -619,3 +619,45 @@ def test_stream_and_resident_api(gpu_matcher):
         assert ptr != 0 and n == 40
     finally:
         gpu_matcher.set_stream(None)
+
+
+def test_cpp_batch_runner_equals_python_path(gpu_matcher, tmp_path):
+    """The C++ host path (dpgicp_shim.hpp + dpg_batch_runner: scan log -> enumerate -> guesses -> one batch -> CSV) gives
+    the same records as the Python mirror driving the same C ABI."""
+    import os
+    import struct
+    import subprocess
+    from dpg_slam_b200.scanmatch import relative_guess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "dpg_slam_b200", "dpg_batch_runner")
+    log, csv_path = str(tmp_path / "scans.bin"), str(tmp_path / "out.csv")
+    r = subprocess.run([exe, "--synthetic", "corridor", "--scans", "60", "--passes", "2", "--beams", "541", "--cov-mode", "2",
+                        "--write-log", log, "--out", csv_path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    import json
+    summary = json.loads(r.stdout.strip().splitlines()[-1])
+    # read the scan log (format documented in dpg_batch_runner.cc)
+    raw = open(log, "rb").read()
+    assert raw[:8] == b"DPGSCAN1"
+    n_scans, n_beams = struct.unpack_from("<ii", raw, 8)
+    amin, amax, rmax, lx, ly, lt = struct.unpack_from("<6f", raw, 16)
+    rec_bytes = 12 + 4 + 4 * n_beams
+    est = np.zeros((n_scans, 3), np.float32); passes = np.zeros(n_scans, np.int32); ranges = np.zeros((n_scans, n_beams), np.float32)
+    for s in range(n_scans):
+        o = 40 + s * rec_bytes
+        est[s] = struct.unpack_from("<3f", raw, o)
+        passes[s] = struct.unpack_from("<i", raw, o + 12)[0]
+        ranges[s] = np.frombuffer(raw, np.float32, n_beams, o + 16)
+    sc = synth.Scanner(n_beams=n_beams, angle_min=amin, angle_max=amax, range_max=rmax, laser_x=lx, laser_y=ly, laser_theta=lt)
+    gpu_matcher.upload_ranges(ranges, sc)
+    src, tgt = gpu_matcher.enumerate_pairs(est[:, :2], passes, 5.0, 2.0)
+    guess = np.stack([relative_guess(est[t], est[s]) for s, t in zip(src, tgt)])
+    p = Params.defaults(cov_mode=COV_CENSI_CORR)                                   # runner defaults + --cov-mode 2
+    got = gpu_matcher.submit_pairs(src, tgt, guess, p)
+    rows = [ln.split(",") for ln in open(csv_path).read().strip().splitlines()[1:]]
+    assert len(rows) == len(src) == summary["pairs"]
+    for k, row in enumerate(rows):
+        assert int(row[0]) == src[k] and int(row[1]) == tgt[k]
+        assert np.float32(row[2]) == got["tx"][k] and np.float32(row[3]) == got["ty"][k] and np.float32(row[4]) == got["theta"][k]
+        assert np.array_equal(np.array(row[5:14], np.float64), got["cov"][k])
+        assert int(row[14]) == got["iterations"][k] and int(row[15]) == got["status"][k]
