@@ -105,7 +105,7 @@ EXPORTS = [
     "dpgicp_set_pairs", "dpgicp_set_pair_cost_hints", "dpgicp_run", "dpgicp_fetch_results", "dpgicp_fetch_factors", "dpgicp_results_device_ptr",
     "dpgicp_gather_export", "dpgicp_gather_attach", "dpgicp_gather_detach", "dpgicp_gather_fetch",
     "dpgicp_gather_device_ptr", "dpgicp_last_run_counters", "dpgicp_single_pair", "dpgicp_cov", "dpgicp_cov_pairs", "dpgicp_correspondences",
-    "dpgicp_enumerate_pairs", "dpgicp_relative_guess", "dpgicp_fp32_probe",
+    "dpgicp_enumerate_pairs", "dpgicp_relative_guess", "dpgicp_fp32_probe", "dpgicp_fp32x2_probe",
 ]
 
 _lib = None
@@ -161,6 +161,7 @@ def load_library() -> C.CDLL:
         "dpgicp_correspondences": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, vp, vp]),
         "dpgicp_relative_guess": (C.c_int, [vp, vp, vp]),
         "dpgicp_fp32_probe": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "dpgicp_fp32x2_probe": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "dpgicp_enumerate_pairs": (C.c_int, [vp, vp, vp, i32, C.c_float, C.c_float, vp, vp,
                                               C.POINTER(i64)]),
     }

@@ -1105,4 +1105,31 @@ int dpgicp_fp32_probe(dpgicp_ctx *ctx, double *mul_add, double *fma) {
   return DPGICP_OK;
 }
 
+int dpgicp_fp32x2_probe(dpgicp_ctx *ctx, double *mul_add_packed) {
+  if (!ctx || !mul_add_packed) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = reserve(ctx, ctx->misc, 256))) return rc;
+  cudaEvent_t e0, e1;
+  CU_TRY(ctx, cudaEventCreate(&e0));
+  CU_TRY(ctx, cudaEventCreate(&e1));
+  const int iters = 1 << 14, blocks = ctx->sm_count * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {             /* rep 0 warms up */
+    CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    fp32x2_probe_kernel<<<blocks, threads, 0, ctx->stream>>>((float *)ctx->misc.p, iters, 1.0000001f, 1e-7f);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    CU_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    const double ops = (double)blocks * threads * (double)iters * 8.0 * 4.0;   /* FMUL2 + FADD2 = 4 operations */
+    if (rep > 0 && ms > 0.f) best = std::max(best, ops / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *mul_add_packed = best;
+  return DPGICP_OK;
+}
+
 }  /* extern "C" */

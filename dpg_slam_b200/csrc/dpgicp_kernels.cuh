@@ -126,6 +126,37 @@ __device__ __forceinline__ float2 xform(float c, float s, float tx, float ty, fl
   return r;
 }
 
+/* ---- packed binary32 pairs (sm_100 FADD2 / FMUL2): one issue slot for two individually rounded
+ * operations; each half is the IEEE round-to-nearest result of the scalar instruction, so the bits are
+ * those of __fsub_rn / __fmul_rn.  A float2 / half of a float4 loaded by LDS.64/.128 already sits in an
+ * aligned register pair, so packing is free. ------------------------------------------------------ */
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+/* dist2(q, p) with q = (qx, qy), p = (px, py) packed: (qx - px)^2 + (qy - py)^2, same roundings as dist2() */
+__device__ __forceinline__ float dist2_packed(f32x2 q, f32x2 p) {
+  const f32x2 d = sub2(q, p);
+  float sx, sy;
+  unpack2(mul2(d, d), sx, sy);
+  return __fadd_rn(sx, sy);
+}
+
 /* Blackwell warp-wide float min/max in one instruction (SASS CREDUX.MIN/MAX.F32) */
 __device__ __forceinline__ float warp_min(float v) {
   float r;
@@ -150,16 +181,24 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 }
 
 /* lower bound of dist2(q, p) over all p in box b = (lox, loy, hix, hiy); same rounding sequence */
-__device__ __forceinline__ float lb_point_box(float qx, float qy, float4 b) {
-  const float ex = fmaxf(fmaxf(__fsub_rn(b.x, qx), __fsub_rn(qx, b.z)), 0.0f);
-  const float ey = fmaxf(fmaxf(__fsub_rn(b.y, qy), __fsub_rn(qy, b.w)), 0.0f);
-  return __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+__device__ __forceinline__ float lb_point_box(f32x2 q, float4 b) {
+  float lx, ly, hx, hy;
+  unpack2(sub2(pack2(b.x, b.y), q), lx, ly);
+  unpack2(sub2(q, pack2(b.z, b.w)), hx, hy);
+  const f32x2 e = pack2(fmaxf(fmaxf(lx, hx), 0.0f), fmaxf(fmaxf(ly, hy), 0.0f));
+  float sx, sy;
+  unpack2(mul2(e, e), sx, sy);
+  return __fadd_rn(sx, sy);
 }
 /* lower bound over all q in box a, p in box b */
 __device__ __forceinline__ float lb_box_box(float4 a, float4 b) {
-  const float ex = fmaxf(fmaxf(__fsub_rn(b.x, a.z), __fsub_rn(a.x, b.z)), 0.0f);
-  const float ey = fmaxf(fmaxf(__fsub_rn(b.y, a.w), __fsub_rn(a.y, b.w)), 0.0f);
-  return __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+  float lx, ly, hx, hy;
+  unpack2(sub2(pack2(b.x, b.y), pack2(a.z, a.w)), lx, ly);
+  unpack2(sub2(pack2(a.x, a.y), pack2(b.z, b.w)), hx, hy);
+  const f32x2 e = pack2(fmaxf(fmaxf(lx, hx), 0.0f), fmaxf(fmaxf(ly, hy), 0.0f));
+  float sx, sy;
+  unpack2(mul2(e, e), sx, sy);
+  return __fadd_rn(sx, sy);
 }
 
 /* ---- mbarrier + 1-D TMA bulk copy (SASS UBLKCP) ------------------------------------------------ */
@@ -193,6 +232,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+/* shared-memory loads from 32-bit shared-window addresses held in registers: the hot loops index the clouds and
+ * boxes from bases computed once per search instead of re-deriving the window base in every iteration */
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float4 lds128_off(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF) : "memory");
+  return v;
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -285,7 +338,7 @@ __device__ __forceinline__ void store_tile_boxes(float2 p, bool valid, int tile,
 struct SearchStats {
   unsigned scans = 0, tests = 0;
 #ifdef DPGICP_STATS
-  unsigned cands = 0, loose = 0, searches = 0;
+  unsigned cands = 0, loose = 0, searches = 0, updates = 0;
 #endif
 };
 
@@ -300,6 +353,8 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
                                           int n_groups, float qx, float qy, bool active, float4 qbox,
                                           float &bd, int &bj, SearchStats &st, float gate) {
   const int lane = threadIdx.x & 31;
+  const uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
+  const f32x2 q2 = pack2(qx, qy);
   float bmax = 0.0f;
   if (PRUNED) bmax = warp_max(active ? bd : -1.0f);
 #ifdef DPGICP_STATS
@@ -310,8 +365,9 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
     unsigned mask;
     if (PRUNED) {
       const int g = base + lane;
-      bool cand = false;
-      if (g < n_groups) cand = lb_box_box(qbox, boxes[g]) <= bmax;
+      /* no branch around the test: a lane past the last group reads whatever follows the boxes in this CTA's
+       * shared memory (at most 32 slots further, always inside the allocation) and is masked out */
+      const bool cand = (lb_box_box(qbox, lds128(a_boxes + g * 16)) <= bmax) & (g < n_groups);
       mask = __ballot_sync(0xffffffffu, cand);
       ++st.tests;
 #ifdef DPGICP_STATS
@@ -325,37 +381,33 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
       const int g = base + __ffs(mask) - 1;
       mask &= mask - 1;
       if (PRUNED) {
-        const bool need = active && (lb_point_box(qx, qy, boxes[g]) <= bd);
+        const bool need = (lb_point_box(q2, lds128(a_boxes + g * 16)) <= bd) & active;
         if (!__any_sync(0xffffffffu, need)) continue;
       }
       ++st.scans;
-      const float4 *pp = reinterpret_cast<const float4 *>(cloud + g * kGroup);
-#ifdef DPGICP_DUAL_CHAIN
-      /* two independent (d2, index) chains (even / odd points) halve the dependent-compare latency;
-       * merged lexicographically, so the result is the first minimum as before */
-      float gd = __int_as_float(0x7f800000), hd = gd;
-      int gj = 0, hj = 1;
-#pragma unroll
-      for (int t = 0; t < kGroup / 2; ++t) {
-        const float4 p = pp[t];                       /* two points per LDS.128, broadcast       */
-        const float d0 = dist2(qx, qy, p.x, p.y);
-        const float d1 = dist2(qx, qy, p.z, p.w);
-        if (d0 < gd) { gd = d0; gj = 2 * t; }
-        if (d1 < hd) { hd = d1; hj = 2 * t + 1; }
-      }
-      if (hd < gd || (hd == gd && hj < gj)) { gd = hd; gj = hj; }
-#else
+      const uint32_t a_grp = a_cloud + g * (kGroup * 8);
+      /* all kGroup distances with packed arithmetic (3 instructions each), their minimum by a tree of
+       * three-input minima; the (d2, index) bookkeeping runs only when some lane can improve or tie */
+      float dd[kGroup];
       float gd = __int_as_float(0x7f800000);
-      int gj = 0;
-#pragma unroll
-      for (int t = 0; t < kGroup / 2; ++t) {
-        const float4 p = pp[t];                       /* two points per LDS.128, broadcast       */
-        const float d0 = dist2(qx, qy, p.x, p.y);
-        const float d1 = dist2(qx, qy, p.z, p.w);
-        if (d0 < gd) { gd = d0; gj = 2 * t; }
-        if (d1 < gd) { gd = d1; gj = 2 * t + 1; }
+#define DPG_SCAN2(T)                                                                                  \
+      if (2 * (T) < kGroup) {                                                                         \
+        const float4 p = lds128_off<16 * (T)>(a_grp);     /* two points per LDS.128, broadcast */     \
+        dd[(2 * (T)) % kGroup] = dist2_packed(q2, pack2(p.x, p.y));                                   \
+        dd[(2 * (T) + 1) % kGroup] = dist2_packed(q2, pack2(p.z, p.w));                               \
+        gd = fminf(fminf(gd, dd[(2 * (T)) % kGroup]), dd[(2 * (T) + 1) % kGroup]);                     \
       }
+      DPG_SCAN2(0) DPG_SCAN2(1) DPG_SCAN2(2) DPG_SCAN2(3) DPG_SCAN2(4) DPG_SCAN2(5) DPG_SCAN2(6) DPG_SCAN2(7)
+      DPG_SCAN2(8) DPG_SCAN2(9) DPG_SCAN2(10) DPG_SCAN2(11) DPG_SCAN2(12) DPG_SCAN2(13) DPG_SCAN2(14) DPG_SCAN2(15)
+#undef DPG_SCAN2
+      if (!__any_sync(0xffffffffu, active && gd <= bd)) continue;
+#ifdef DPGICP_STATS
+      st.updates++;
 #endif
+      int gj = kGroup - 1;                              /* first index attaining the minimum       */
+#pragma unroll
+      for (int t = kGroup - 2; t >= 0; --t)
+        if (dd[t] == gd) gj = t;
       const int j = g * kGroup + gj;
       if (gd < bd || (gd == bd && j < bj)) { bd = gd; bj = j; }
     }
@@ -1289,6 +1341,26 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float *out, int iters, 
 #pragma unroll
   for (int k = 0; k < 8; ++k) s += x[k];
   if (s == 123.456f) out[0] = s;       /* keeps the chains alive; practically never true */
+}
+
+/* the same chains with packed pairs: FMUL2 + FADD2 (two individually rounded results per instruction) */
+__global__ void __launch_bounds__(256) fp32x2_probe_kernel(float *out, int iters, float a, float b) {
+  f32x2 x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = pack2((float)(threadIdx.x + k) * 1e-3f, (float)(threadIdx.x + k) * 2e-3f);
+  const f32x2 a2 = pack2(a, a), b2 = pack2(b, b);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      f32x2 r;
+      asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(mul2(x[k], a2)), "l"(b2));
+      x[k] = r;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { float lo, hi; unpack2(x[k], lo, hi); s += lo + hi; }
+  if (s == 123.456f) out[0] = s;
 }
 
 }  // namespace dpg

@@ -231,7 +231,9 @@ class ScanMatcher:
         """Measured FP32 CUDA-core rates of this GPU (ops/s): separately rounded FMUL+FADD and FFMA."""
         a, b = C.c_double(0), C.c_double(0)
         self._check(self._lib.dpgicp_fp32_probe(self._h, C.byref(a), C.byref(b)))
-        return {"mul_add_ops_per_s": a.value, "fma_ops_per_s": b.value}
+        p = C.c_double(0)
+        self._check(self._lib.dpgicp_fp32x2_probe(self._h, C.byref(p)))
+        return {"mul_add_ops_per_s": a.value, "fma_ops_per_s": b.value, "mul_add_packed_ops_per_s": p.value}
 
     # ---- the two reference call shapes ----------------------------------------------------------------
     def run_icp(self, node_1_cloud, node_2_cloud, guess, params: Optional[Params] = None):

@@ -257,6 +257,9 @@ int  dpgicp_enumerate_pairs(dpgicp_ctx *ctx, const float *node_xy, const int32_t
  * the roofline of the distance loop: separately rounded FMUL+FADD (what the bit-exact loop may use)
  * and FFMA (for context).  Results in operations per second (one FMUL, FADD or FFMA = 1 op).     */
 int  dpgicp_fp32_probe(dpgicp_ctx *ctx, double *ops_per_s_mul_add, double *ops_per_s_fma);
+/* The same FMUL+FADD chains issued as packed pairs (sm_100 FMUL2 / FADD2, what the distance loop uses):
+ * operations per second, one packed instruction = 2 operations.                                   */
+int  dpgicp_fp32x2_probe(dpgicp_ctx *ctx, double *ops_per_s_mul_add_packed);
 
 #ifdef __cplusplus
 }

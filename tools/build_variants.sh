@@ -6,12 +6,12 @@ build() { name=$1; shift; $NV "$@" -Xptxas -v -o ../libdpgicp_$name.so dpgicp_ab
 build tw20 -DDPGICP_TARGET_WARPS=20
 build tw24 -DDPGICP_TARGET_WARPS=24
 build tw32 -DDPGICP_TARGET_WARPS=32
-build tw24d -DDPGICP_TARGET_WARPS=24 -DDPGICP_DUAL_CHAIN
-build tw32d -DDPGICP_TARGET_WARPS=32 -DDPGICP_DUAL_CHAIN
+
+
 build tw24g32 -DDPGICP_TARGET_WARPS=24 -DDPGICP_GROUP=32
-build tw24g32d -DDPGICP_TARGET_WARPS=24 -DDPGICP_GROUP=32 -DDPGICP_DUAL_CHAIN
+
 wait
-for n in tw20 tw24 tw32 tw24d tw32d tw24g32 tw24g32d; do echo == $n; python3 - $n <<'PY'
+for n in tw20 tw24 tw32 tw24g32; do echo == $n; python3 - $n <<'PY'
 import re,sys
 t=open(f'/tmp/ptxas_{sys.argv[1]}.txt').read()
 for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'\nptxas info    : Function properties for \S+\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\nptxas info    : Used (\d+) registers", t):

@@ -15,7 +15,10 @@ wl = synth.config_corridor(n_pairs=n_pairs, seed=2) if which == "corridor" else 
 tag = os.path.basename(os.environ.get("DPGICP_LIBRARY", "default")).replace(".so", "")
 out = {}
 for chain in chains:
-    os.environ["DPGICP_CHAIN"] = chain
+    if chain == "default":
+        os.environ.pop("DPGICP_CHAIN", None)       # the library's own stage chain
+    else:
+        os.environ["DPGICP_CHAIN"] = chain
     stages, warps, ctas = chain.replace(",", "-"), 0, 0
     with ScanMatcher(0) as sm:
         sm.upload_ranges(wl.ranges, wl.scanner)
