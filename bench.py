@@ -48,6 +48,7 @@ WORKLOADS = {
                   pairs_per_gpu=125_000, beams=4096, seed=4, metric=1),
 }
 WORKLOAD = "corridor"
+SEARCH = "pruned"            # --search projective: the approximate beam-order search (north-star extension), not the headline
 PAIRS_PER_GPU = WORKLOADS[WORKLOAD]["pairs_per_gpu"]
 N_BEAMS = WORKLOADS[WORKLOAD]["beams"]
 
@@ -71,8 +72,9 @@ def make_workload(n_pairs: int):
 
 
 def bench_params():
-    from dpg_slam_b200._abi import COV_CENSI_CORR, Params
-    return Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR, metric=WORKLOADS[WORKLOAD]["metric"])
+    from dpg_slam_b200._abi import COV_CENSI_CORR, SEARCH_PROJECTIVE, SEARCH_PRUNED, Params
+    return Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR, metric=WORKLOADS[WORKLOAD]["metric"],
+                           search=SEARCH_PROJECTIVE if SEARCH == "projective" else SEARCH_PRUNED)
 
 
 def workload_config(n_gpus: int, extra=None):
@@ -82,7 +84,9 @@ def workload_config(n_gpus: int, extra=None):
            "fov_deg": 270, "downsample_divisor": 1, "metric_kind": "point_to_line" if w["metric"] else "point_to_point",
            "reciprocal": True,
            "cov_mode": "CENSI_CORR(cap 200)", "max_iterations": 500, "max_correspondence_distance_m": 0.6,
-           "search": "exact pruned (bounding-box groups)", "sharding": f"round-robin over {n_gpus} GPU(s), scan store replicated",
+           "search": ("exact pruned (bounding-box groups)" if SEARCH == "pruned" else
+                      "PROJECTIVE (approximate: beam-order projection, window 8 each side; not the reference's exact search)"),
+           "sharding": f"round-robin over {n_gpus} GPU(s), scan store replicated",
            "l2": "flushed between timed steps (512 MiB memset outside the event pair)", "seed": w["seed"]}
     if extra:
         cfg.update(extra)
@@ -432,8 +436,11 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="corridor", choices=sorted(WORKLOADS))
+    ap.add_argument("--search", default="pruned", choices=["pruned", "projective"])
     args = ap.parse_args()
     select_workload(args.workload)
+    global SEARCH
+    SEARCH = args.search
     if args.impl == "reference":
         return run_reference(args)
     return run_product(args)

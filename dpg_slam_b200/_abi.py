@@ -14,9 +14,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 # ---- constants (include/dpgicp.h) -----------------------------------------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 METRIC_POINT_TO_POINT, METRIC_POINT_TO_LINE = 0, 1
-SEARCH_BRUTE, SEARCH_PRUNED = 0, 1
+SEARCH_BRUTE, SEARCH_PRUNED, SEARCH_PROJECTIVE = 0, 1, 2
 COV_REFERENCE_LIVE, COV_CENSI_INDEXPAIR, COV_CENSI_CORR = 0, 1, 2
 STOP_MASK = 0xFF
 STOP_NONE, STOP_ITERATIONS, STOP_TRANSFORM, STOP_ABS_MSE, STOP_NO_CORRESPONDENCES, STOP_DEGENERATE = 0, 1, 2, 3, 4, 5
@@ -47,7 +47,9 @@ class Params(C.Structure):
         ("laser_x_variance", C.c_float),
         ("laser_y_variance", C.c_float),
         ("laser_theta_variance", C.c_float),
-        ("reserved0", C.c_int32),
+        ("projective_window", C.c_int32),
+        ("sensor_x", C.c_float),
+        ("sensor_y", C.c_float),
     ]
 
     @classmethod
@@ -57,7 +59,7 @@ class Params(C.Structure):
                 metric=METRIC_POINT_TO_POINT, search=SEARCH_PRUNED, cov_mode=COV_REFERENCE_LIVE,
                 cov_cap=200, transformation_epsilon=5e-9, max_correspondence_distance=0.6,
                 cov_sensor_variance=0.01, laser_x_variance=0.5, laser_y_variance=0.5,
-                laser_theta_variance=0.3, reserved0=0)
+                laser_theta_variance=0.3, projective_window=8, sensor_x=0.2, sensor_y=0.0)
         for k, v in overrides.items():
             if not hasattr(p, k):
                 raise AttributeError(f"dpgicp_params has no field {k!r}")
@@ -96,7 +98,7 @@ FACTOR_DTYPE = np.dtype([
 ], align=True)
 
 assert C.sizeof(Result) == 112 and RESULT_DTYPE.itemsize == 112 and FACTOR_DTYPE.itemsize == 96
-assert C.sizeof(Params) == 72
+assert C.sizeof(Params) == 80
 
 EXPORTS = [
     "dpgicp_abi_version", "dpgicp_default_params", "dpgicp_create", "dpgicp_destroy",

@@ -120,8 +120,15 @@ int check_params(dpgicp_ctx *ctx, const dpgicp_params *p) {
   if (!(p->transformation_epsilon >= 0.0)) return fail(ctx, DPGICP_E_INVALID, "transformation_epsilon must be >= 0");
   if (p->metric != DPGICP_METRIC_POINT_TO_POINT && p->metric != DPGICP_METRIC_POINT_TO_LINE)
     return fail(ctx, DPGICP_E_INVALID, "metric must be DPGICP_METRIC_POINT_TO_POINT or DPGICP_METRIC_POINT_TO_LINE");
-  if (p->search != DPGICP_SEARCH_BRUTE && p->search != DPGICP_SEARCH_PRUNED)
-    return fail(ctx, DPGICP_E_INVALID, "search must be DPGICP_SEARCH_BRUTE or DPGICP_SEARCH_PRUNED");
+  if (p->search != DPGICP_SEARCH_BRUTE && p->search != DPGICP_SEARCH_PRUNED && p->search != DPGICP_SEARCH_PROJECTIVE)
+    return fail(ctx, DPGICP_E_INVALID, "search must be DPGICP_SEARCH_BRUTE, DPGICP_SEARCH_PRUNED or DPGICP_SEARCH_PROJECTIVE");
+  if (p->search == DPGICP_SEARCH_PROJECTIVE) {
+    if (p->projective_window < 1 || p->projective_window > 1024)
+      return fail(ctx, DPGICP_E_INVALID, "projective_window must be in 1..1024");
+    if (!std::isfinite(p->sensor_x) || !std::isfinite(p->sensor_y) || std::fabs(p->sensor_x) > DPGICP_MAX_ABS_COORD ||
+        std::fabs(p->sensor_y) > DPGICP_MAX_ABS_COORD)
+      return fail(ctx, DPGICP_E_INVALID, "sensor_x / sensor_y must be finite and within DPGICP_MAX_ABS_COORD");
+  }
   if (p->cov_mode < DPGICP_COV_REFERENCE_LIVE || p->cov_mode > DPGICP_COV_CENSI_CORR)
     return fail(ctx, DPGICP_E_INVALID, "cov_mode out of range");
   if (p->cov_cap < 0) return fail(ctx, DPGICP_E_INVALID, "cov_cap must be >= 0");
@@ -137,9 +144,9 @@ float gate_threshold(const dpgicp_params *p) {
   return f;
 }
 
-template <int WARPS, bool PRUNED, int CSIZE>
+template <int WARPS, int SEARCH, int CSIZE>
 int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t max_items, int nw, int *grid_out) {
-  auto kern = icp_pairs_kernel<WARPS, PRUNED, CSIZE>;
+  auto kern = icp_pairs_kernel<WARPS, SEARCH, CSIZE>;
   CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3((unsigned)nw * 32, 1, 1);
@@ -181,22 +188,24 @@ int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t m
 
 /* nw warps per CTA run on the instantiation with the next power-of-two register budget; clusters (the last
  * stage only) use the 16-warp budget */
-template <bool PRUNED>
+template <int SEARCH>
 int launch_icp_w(dpgicp_ctx *ctx, int nw, int csize, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
   nw = std::max(1, std::min(nw, 16));
   /* first stage of large scans: 12 warps with the 80-register budget so that two CTAs share an SM */
-  if (csize == 1 && !kp.resume && nw > 8 && nw <= 12) return launch_icp_t<12, PRUNED, 1>(ctx, kp, smem, n, nw, grid_out);
-  if (csize == 2) return launch_icp_t<16, PRUNED, 2>(ctx, kp, smem, n, nw, grid_out);
-  if (csize == 4) return launch_icp_t<16, PRUNED, 4>(ctx, kp, smem, n, nw, grid_out);
-  if (nw <= 1) return launch_icp_t<1, PRUNED, 1>(ctx, kp, smem, n, 1, grid_out);
-  if (nw <= 2) return launch_icp_t<2, PRUNED, 1>(ctx, kp, smem, n, nw, grid_out);
-  if (nw <= 4) return launch_icp_t<4, PRUNED, 1>(ctx, kp, smem, n, nw, grid_out);
-  if (nw <= 8) return launch_icp_t<8, PRUNED, 1>(ctx, kp, smem, n, nw, grid_out);
-  return launch_icp_t<16, PRUNED, 1>(ctx, kp, smem, n, nw, grid_out);
+  if (csize == 1 && !kp.resume && nw > 8 && nw <= 12) return launch_icp_t<12, SEARCH, 1>(ctx, kp, smem, n, nw, grid_out);
+  if (csize == 2) return launch_icp_t<16, SEARCH, 2>(ctx, kp, smem, n, nw, grid_out);
+  if (csize == 4) return launch_icp_t<16, SEARCH, 4>(ctx, kp, smem, n, nw, grid_out);
+  if (nw <= 1) return launch_icp_t<1, SEARCH, 1>(ctx, kp, smem, n, 1, grid_out);
+  if (nw <= 2) return launch_icp_t<2, SEARCH, 1>(ctx, kp, smem, n, nw, grid_out);
+  if (nw <= 4) return launch_icp_t<4, SEARCH, 1>(ctx, kp, smem, n, nw, grid_out);
+  if (nw <= 8) return launch_icp_t<8, SEARCH, 1>(ctx, kp, smem, n, nw, grid_out);
+  return launch_icp_t<16, SEARCH, 1>(ctx, kp, smem, n, nw, grid_out);
 }
 
-int launch_stage(dpgicp_ctx *ctx, bool pruned, int nw, int csize, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
-  return pruned ? launch_icp_w<true>(ctx, nw, csize, kp, smem, n, grid_out) : launch_icp_w<false>(ctx, nw, csize, kp, smem, n, grid_out);
+int launch_stage(dpgicp_ctx *ctx, int search, int nw, int csize, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
+  if (search == DPGICP_SEARCH_PROJECTIVE) return launch_icp_w<DPGICP_SEARCH_PROJECTIVE>(ctx, nw, csize, kp, smem, n, grid_out);
+  if (search == DPGICP_SEARCH_PRUNED) return launch_icp_w<DPGICP_SEARCH_PRUNED>(ctx, nw, csize, kp, smem, n, grid_out);
+  return launch_icp_w<DPGICP_SEARCH_BRUTE>(ctx, nw, csize, kp, smem, n, grid_out);
 }
 
 /* warps per CTA close to `target` that split `tiles` 32-point tiles evenly (every warp gets
@@ -249,8 +258,11 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
     kp.gather_rank = ctx->gather_rank;
     for (int g = 0; g < ctx->gather_world; ++g) kp.gather_peer[g] = (dpgicp_result *)ctx->gather_peer[g];
   }
-  const size_t smem = smem_bytes(n_cap);
-  const bool pruned = p->search == DPGICP_SEARCH_PRUNED;
+  kp.proj_window = p->projective_window;
+  kp.sensor_x = p->sensor_x;
+  kp.sensor_y = p->sensor_y;
+  const size_t smem = smem_bytes(n_cap, p->search == DPGICP_SEARCH_PROJECTIVE);
+  const int search = p->search;
 
   /* stage widths (warps per pair): narrow CTAs for the bulk of the batch, wider ones for the pairs
    * still running when a stage's queue runs dry; each width is balanced against the tile count */
@@ -283,7 +295,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   if (n_stages > 1) {
     /* every stage can suspend at most one pair per CTA: size the state slots for stage 0's grid */
     int g0 = -1;
-    int rc = launch_stage(ctx, pruned, shapes[0].warps, shapes[0].csize, kp, smem, b.n_pairs, &g0);
+    int rc = launch_stage(ctx, search, shapes[0].warps, shapes[0].csize, kp, smem, b.n_pairs, &g0);
     if (rc) return rc;
     for (int k = 0; k < 2; ++k) {
       if ((rc = reserve(ctx, ctx->state[k], (size_t)g0 * (size_t)kp.slot_bytes))) return rc;
@@ -308,7 +320,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
     }
     int grid = 0;
     const int64_t max_items = sidx == 0 ? b.n_pairs : (int64_t)grid_prev;
-    int rc = launch_stage(ctx, pruned, shapes[sidx].warps, shapes[sidx].csize, ks, smem, max_items, &grid);
+    int rc = launch_stage(ctx, search, shapes[sidx].warps, shapes[sidx].csize, ks, smem, max_items, &grid);
     if (rc) return rc;
     grid_prev = grid;
   }
@@ -487,6 +499,9 @@ int dpgicp_default_params(dpgicp_params *p) {
   p->laser_x_variance = 0.5f;               /* parameters.h:374 */
   p->laser_y_variance = 0.5f;               /* parameters.h:385 */
   p->laser_theta_variance = 0.3f;           /* parameters.h:396 */
+  p->projective_window = 8;                 /* DPGICP_SEARCH_PROJECTIVE only */
+  p->sensor_x = 0.2f;                       /* parameters.h:319-339: laser at (0.2, 0, 0) in base_link */
+  p->sensor_y = 0.0f;
   return DPGICP_OK;
 }
 

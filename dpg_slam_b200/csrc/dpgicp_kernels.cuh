@@ -86,6 +86,8 @@ struct KernelParams {
   long long n_pairs;
   int32_t n_cap;                  /* smem capacity per cloud in points, multiple of 32            */
   int32_t max_iterations, use_reciprocal, divisor, metric, cov_mode, cov_cap;
+  int32_t proj_window;            /* DPGICP_SEARCH_PROJECTIVE: candidates on each side of the projected index */
+  float sensor_x, sensor_y;       /* ... and the laser origin the beam order turns around                      */
   float gate;                     /* binary32 floor of max_correspondence_distance^2              */
   double eps, rot_thr, sensor_var;
   float live[3];
@@ -267,12 +269,15 @@ struct SmemLayout {
   float *step;      /* 4 */
   int32_t *ctl;     /* [0] item lo [1] item hi [2] stop [3] K [4] slot                               */
   uint64_t *mbar;
+  float *fin;       /* 4: accumulated transform (c, s, tx, ty), read by the projective reciprocal test   */
+  float *tkey;      /* projective search only: n_cap beam-order keys of the target ...                    */
+  float *skey;      /* ... and of the untransformed source                                                */
 };
 
-__host__ __device__ inline size_t smem_bytes(int n_cap) {
+__host__ __device__ inline size_t smem_bytes(int n_cap, bool projective) {
   const int g = n_cap / kGroup, t = n_cap / kTile;
   return (size_t)n_cap * (8 + 8 + 4) + (size_t)g * (16 + 16) + (size_t)t * (16 + 4) + 48 * 8 + kMaxWarps * 12 * 8 + 16 + 32 +
-         16 + 64;
+         16 + 64 + 16 + (projective ? (size_t)n_cap * 8 : 0);
 }
 
 __device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap) {
@@ -291,6 +296,9 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap) {
   L.tcnt = (int32_t *)(base + o); o += (size_t)t * 4;
   L.step = (float *)(base + o);   o += 16;
   L.ctl = (int32_t *)(base + o);  o += 32;
+  L.fin = (float *)(base + o);    o += 16;
+  L.tkey = (float *)(base + o);   o += (size_t)n_cap * 4;     /* present only when launched for the projective search */
+  L.skey = (float *)(base + o);
   return L;
 }
 
@@ -336,7 +344,7 @@ __device__ __forceinline__ void store_tile_boxes(float2 p, bool valid, int tile,
 
 /* executed-work counters kept in registers by every warp, flushed once per CTA */
 struct SearchStats {
-  unsigned scans = 0, tests = 0;
+  unsigned scans = 0, tests = 0, window_evals = 0;   /* window_evals: per lane (projective search) */
 #ifdef DPGICP_STATS
   unsigned cands = 0, loose = 0, searches = 0, updates = 0;
 #endif
@@ -420,6 +428,69 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
  * PCL determineReciprocalCorrespondences (App. A.3-2): forward NN within the gate, then the target
  * point's own nearest source point must be the query ((d2, index)-lexicographic, like the forward).
  * ---------------------------------------------------------------------------------------------- */
+/* ---- DPGICP_SEARCH_PROJECTIVE (include/dpgicp.h; defined by oracle/dpg_oracle.c correspondences_projective) ---- */
+/* bearing key of a point seen from the laser origin: monotone in atan2 on (-pi, pi], no libm, IEEE division */
+__device__ __forceinline__ float beam_key(float px, float py, float ox, float oy) {
+  const float vx = __fsub_rn(px, ox), vy = __fsub_rn(py, oy);
+  const float a = __fadd_rn(fabsf(vx), fabsf(vy));
+  const float t = a > 0.0f ? __fdiv_rn(vy, a) : 0.0f;
+  if (vx >= 0.0f) return t;
+  return vy >= 0.0f ? __fsub_rn(2.0f, t) : __fsub_rn(-2.0f, t);
+}
+/* plain bisection over the stored order */
+__device__ __forceinline__ int key_lower_bound(const float *keys, int n, float k) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] < k) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+/* (d2, index) argmin of (qx, qy) over cloud[c - W, c + W) clipped to [0, n): ascending scan, strict improvement */
+__device__ __forceinline__ void nn_window(const float2 *cloud, int n, int c, int W, float qx, float qy, float &bd, int &bj,
+                                          SearchStats &st) {
+  const int j0 = c - W < 0 ? 0 : c - W, j1 = c + W > n ? n : c + W;
+  const f32x2 q2 = pack2(qx, qy);
+  bd = __int_as_float(0x7f800000);
+  bj = -1;
+  for (int j = j0; j < j1; ++j) {
+    const float2 p = cloud[j];
+    const float d = dist2_packed(q2, pack2(p.x, p.y));
+    if (d < bd) { bd = d; bj = j; }
+  }
+  st.window_evals += (unsigned)(j1 > j0 ? j1 - j0 : 0);
+}
+
+/* one correspondence pass of one source tile, projective search: every lane works alone */
+__device__ __forceinline__ bool match_tile_projective(const SmemLayout &L, int tile, int ns, int nt, float gate,
+                                                      bool reciprocal, int W, float ox, float oy, float2 &q, int &j_out,
+                                                      float &d_out, bool &fwd_ok, SearchStats &st) {
+  const int lane = threadIdx.x & 31;
+  const int i = tile * kTile + lane;
+  const bool valid = i < ns;
+  q = L.src[i];
+  float bd = __int_as_float(0x7f800000);
+  int bj = -1;
+  if (valid) nn_window(L.tgt, nt, key_lower_bound(L.tkey, nt, beam_key(q.x, q.y, ox, oy)), W, q.x, q.y, bd, bj, st);
+  fwd_ok = valid && bj >= 0 && bd <= gate;
+  j_out = bj;
+  d_out = bd;
+  bool accept = fwd_ok;
+  if (reciprocal && fwd_ok) {
+    /* the matched target point in the source scan's own frame: R^T (r - t) */
+    const float2 r = L.tgt[bj];
+    const float fc = L.fin[0], fs = L.fin[1];
+    const float ex = __fsub_rn(r.x, L.fin[2]), ey = __fsub_rn(r.y, L.fin[3]);
+    const float bx = __fadd_rn(__fmul_rn(fc, ex), __fmul_rn(fs, ey));
+    const float by = __fsub_rn(__fmul_rn(fc, ey), __fmul_rn(fs, ex));
+    float rd;
+    int ri;
+    nn_window(L.src, ns, key_lower_bound(L.skey, ns, beam_key(bx, by, ox, oy)), W, r.x, r.y, rd, ri, st);
+    accept = (ri == i) && (rd <= gate);
+  }
+  return accept;
+}
+
 template <bool PRUNED>
 __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns, int n_groups_s,
                                            int n_groups_t, float gate, bool reciprocal, float2 &q,
@@ -454,6 +525,18 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
     accept = fwd_ok && (ri == i);
   }
   return accept;
+}
+
+struct KernelParams;
+/* one correspondence pass of one source tile with the search strategy the kernel was instantiated for */
+template <int SEARCH, typename KP>
+__device__ __forceinline__ bool match_any(const SmemLayout &L, const KP &P, int tile, int ns, int nt, int gs, int gt,
+                                          float2 &q, int &j, float &d, bool &fwd, SearchStats &st) {
+  if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE)
+    return match_tile_projective(L, tile, ns, nt, P.gate, P.use_reciprocal != 0, P.proj_window, P.sensor_x, P.sensor_y, q, j,
+                                 d, fwd, st);
+  else
+    return match_tile<SEARCH == DPGICP_SEARCH_PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd, st);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -635,7 +718,7 @@ __device__ __forceinline__ T *peer_smem(T *p, int rank) {
   else return p;
 }
 
-template <int WARPS, bool PRUNED, int CSIZE>
+template <int WARPS, int SEARCH, int CSIZE>
 __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(const KernelParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SmemLayout L = carve(smem_raw, P.n_cap);
@@ -709,16 +792,33 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
     __syncthreads();
     for (int t = warp; t < tt; t += nw) {
       const int k = t * kTile + lane;
-      store_tile_boxes(L.tgt[k], k < nt, t, L.tbox, nullptr);
+      const float2 p = L.tgt[k];
+      if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) L.tkey[k] = beam_key(p.x, p.y, P.sensor_x, P.sensor_y);
+      else store_tile_boxes(p, k < nt, t, L.tbox, nullptr);
     }
     for (int t = warp; t < ts; t += nw) {
       const int k = t * kTile + lane;
       float2 p = L.src[k];
+      if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) {
+        /* keys of the UNTRANSFORMED source (a resumed pair holds the current one: take the original from the store) */
+        float2 o = p;
+        if (P.resume && k < ns) o = __ldg(srow + (size_t)k * div);
+        L.skey[k] = beam_key(o.x, o.y, P.sensor_x, P.sensor_y);
+      }
       if (!P.resume) {
         if (k < ns) { p = xform(task.c, task.s, task.tx, task.ty, p); L.src[k] = p; }
         L.nn[k] = -1;
       }
-      store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
+      if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
+    }
+    if (SEARCH == DPGICP_SEARCH_PROJECTIVE && tid == 0) {
+      /* accumulated transform the source in shared memory has been moved by so far */
+      if (P.resume) {
+        const SuspHeader h = *reinterpret_cast<const SuspHeader *>(slot_in);
+        L.fin[0] = h.fc; L.fin[1] = h.fs; L.fin[2] = h.ftx; L.fin[3] = h.fty;
+      } else {
+        L.fin[0] = task.c; L.fin[1] = task.s; L.fin[2] = task.tx; L.fin[3] = task.ty;
+      }
     }
     __syncthreads();
 
@@ -726,8 +826,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
     if (P.corr_out != nullptr) {
       for (int tile = warp; tile < ts; tile += nw) {
         float2 q; int j; float d; bool fwd;
-        const bool acc = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
-                                            stats);
+        const bool acc = match_any<SEARCH>(L, P, tile, ns, nt, gs, gt, q, j, d, fwd, stats);
         const int i = tile * kTile + lane;
         if (i < ns) {
           P.corr_out[i] = acc ? j : -1;
@@ -764,8 +863,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       int m_k = 0;
       for (int tile = tile0; tile < ts; tile += tile_stride) {
         float2 q; int j; float d; bool fwd;
-        const bool acc = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
-                                            stats);
+        const bool acc = match_any<SEARCH>(L, P, tile, ns, nt, gs, gt, q, j, d, fwd, stats);
         const int i = tile * kTile + lane;
         if (i < ns) L.nn[i] = fwd ? j : -1;           /* seed of the next pass */
         if (acc) {
@@ -899,6 +997,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           const float ntx = __fadd_rn(__fadd_rn(__fmul_rn(sc, ftx), __fmul_rn(-ss, fty)), stx);
           const float nty = __fadd_rn(__fadd_rn(__fmul_rn(ss, ftx), __fmul_rn(sc, fty)), sty);
           fc = nc; fs = nsn; ftx = ntx; fty = nty;
+          if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) { L.fin[0] = fc; L.fin[1] = fs; L.fin[2] = ftx; L.fin[3] = fty; }
           ++iterations;
           mse = __dmul_rn(__dmul_rn((double)L.red[9], 1.0 / kScaleD2), invK);
           /* DefaultConvergenceCriteria (App. A.5), in PCL's order */
@@ -935,7 +1034,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           const int k = t * kTile + lane;
           float2 p = L.src[k];
           if (k < ns) { p = xform(sc, ss, stx, sty, p); L.src[k] = p; }
-          store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
+          if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
         }
       }
       if (tid == 0 && crank == 0) ++c_iters;
@@ -996,13 +1095,12 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           float2 p = make_float2(kPad, kPad);
           if (k < ns) { p = xform(Tc, Ts, Ttx, Tty, __ldg(srow + (size_t)k * div)); }
           L.src[k] = p;
-          store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
+          if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
         }
         __syncthreads();
         for (int tile = tile0; tile < ts; tile += tile_stride) {
           float2 q; int j; float d; bool fwd;
-          const bool ok = match_tile<PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd,
-                                             stats);
+          const bool ok = match_any<SEARCH>(L, P, tile, ns, nt, gs, gt, q, j, d, fwd, stats);
           const unsigned bal = __ballot_sync(0xffffffffu, ok);
           const int i = tile * kTile + lane;
           if (i < ns) L.nn[i] = ok ? j : -1;
@@ -1091,6 +1189,12 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
   /* executed-work counters (one set of atomics per CTA) */
   if (lane == 0) {
     atomicAdd(P.counters + 2, (unsigned long long)stats.scans * (kGroup * 32ull));
+  }
+  if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) {
+    const unsigned we = __reduce_add_sync(0xffffffffu, stats.window_evals);   /* per-lane counts, may wrap past 2^32 per warp: an executed-work statistic only */
+    if (lane == 0) atomicAdd(P.counters + 2, (unsigned long long)we);
+  }
+  if (lane == 0) {
     atomicAdd(P.counters + 3, (unsigned long long)stats.tests * 32ull);
 #ifdef DPGICP_STATS
     atomicAdd(P.counters + 5, (unsigned long long)stats.cands);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DPGICP_ABI_VERSION 1
+#define DPGICP_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define DPGICP_OK            0
@@ -52,9 +52,21 @@ extern "C" {
                                           * neighbour; one Gauss-Newton step per iteration from the 3x3 normal
                                           * equations (Cholesky); DESIGN.md "point-to-line"               */
 
-/* nearest-neighbour search strategy; both are exact and give identical correspondences */
+/* nearest-neighbour search strategy; BRUTE and PRUNED are exact and give identical correspondences */
 #define DPGICP_SEARCH_BRUTE   0
 #define DPGICP_SEARCH_PRUNED  1          /* beam-order block bounding boxes + seeded bound       */
+#define DPGICP_SEARCH_PROJECTIVE 2       /* north-star extension; no reference counterpart (PCL searches exactly).
+                                          * APPROXIMATE neighbour by projection onto the other scan's beam order:
+                                          *   key(v), v = point - (sensor_x, sensor_y): a = |vx| + |vy|, t = a > 0 ? vy / a : 0,
+                                          *   key = vx >= 0 ? t : (vy >= 0 ? 2 - t : -2 - t)     (binary32, monotone in the bearing)
+                                          *   c = lower_bound of key(query) in the searched scan's keys (plain bisection over the
+                                          *   stored order, whether or not the keys are sorted); candidates = indices
+                                          *   [c - W, c + W) inside the scan, W = projective_window; the (d2, index)-
+                                          *   lexicographic minimum among them is the neighbour.
+                                          * Forward: query = current source point, searched = target.  Reciprocal: query = the
+                                          * matched target point taken back to the source frame by the inverse of the current
+                                          * transform, searched keys = the untransformed source scan, distances to the current
+                                          * source points.  Defined by oracle/dpg_oracle.c (orc_correspondences_ex).      */
 
 /* what is written to result.cov (SURVEY.md §8a "covariance modes") */
 #define DPGICP_COV_REFERENCE_LIVE  0     /* diag(sx2, sy2, st2): cov_func_point_to_point.h:572-575 */
@@ -91,7 +103,9 @@ typedef struct dpgicp_params {
   float   laser_x_variance;            /* 0.5    parameters.h:374 */
   float   laser_y_variance;            /* 0.5    parameters.h:385 */
   float   laser_theta_variance;        /* 0.3    parameters.h:396 */
-  int32_t reserved0;
+  int32_t projective_window;           /* 8      DPGICP_SEARCH_PROJECTIVE only: W, candidates on each side (1..1024)   */
+  float   sensor_x, sensor_y;          /* 0.2, 0 DPGICP_SEARCH_PROJECTIVE only: laser origin in the cloud (base_link)
+                                        *        frame, parameters.h:319-339 — the centre the beam order turns around  */
 } dpgicp_params;
 
 /* ---- fixed-size result record (112 bytes) ------------------------------------------------- */

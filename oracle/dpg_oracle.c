@@ -224,15 +224,91 @@ static inline void nn_grid(const grid_t *g, float qx, float qy, const float *clo
   *best_d = bd;
 }
 
+/* --- DPGICP_SEARCH_PROJECTIVE (include/dpgicp.h): approximate neighbour by projection onto the other
+ * scan's beam order.  North-star extension with no reference counterpart; this text is its definition. */
+
+/* bearing key of v = point - sensor origin: a monotone function of atan2(vy, vx) on (-pi, pi] computed
+ * without libm, in individually rounded binary32 operations (the division is IEEE round-to-nearest) */
+float orc_beam_key(float px, float py, float ox, float oy) {
+  const float vx = px - ox, vy = py - oy;
+  const float a = fabsf(vx) + fabsf(vy);
+  const float t = a > 0.0f ? vy / a : 0.0f;
+  if (vx >= 0.0f) return t;
+  return vy >= 0.0f ? 2.0f - t : -2.0f - t;
+}
+
+/* plain bisection over the stored order (well defined whether or not the keys are sorted) */
+static inline int key_lower_bound(const float *keys, int n, float k) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] < k) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+/* (d2, index) argmin of (qx, qy) over cloud[c - W, c + W) clipped to [0, n) */
+static inline void nn_window(float qx, float qy, const float *cloud, int n, int c, int W, int *best_i, float *best_d) {
+  float bd = INFINITY;
+  int bi = -1;
+  const int j0 = c - W < 0 ? 0 : c - W, j1 = c + W > n ? n : c + W;
+  for (int j = j0; j < j1; ++j) {
+    const float d = dist2(qx, qy, cloud[2 * j], cloud[2 * j + 1]);
+    if (d < bd) { bd = d; bi = j; }
+  }
+  *best_i = bi;
+  *best_d = bd;
+}
+
+static int correspondences_projective(const float *src_t, int ns, const float *tgt, int nt, const dpgicp_params *p,
+                                      const float *src_orig, const float T[4], int32_t *corr, float *d2) {
+  const float thr = gate_threshold(p);
+  const float ox = p->sensor_x, oy = p->sensor_y;
+  const int W = p->projective_window;
+  float *tkey = (float *)malloc(sizeof(float) * (size_t)(nt > 0 ? nt : 1));
+  float *skey = (float *)malloc(sizeof(float) * (size_t)(ns > 0 ? ns : 1));
+  for (int j = 0; j < nt; ++j) tkey[j] = orc_beam_key(tgt[2 * j], tgt[2 * j + 1], ox, oy);
+  for (int i = 0; i < ns; ++i) skey[i] = orc_beam_key(src_orig[2 * i], src_orig[2 * i + 1], ox, oy);
+  int K = 0;
+  for (int i = 0; i < ns; ++i) {
+    int j, ir;
+    float d, dr;
+    corr[i] = -1;
+    const float qx = src_t[2 * i], qy = src_t[2 * i + 1];
+    nn_window(qx, qy, tgt, nt, key_lower_bound(tkey, nt, orc_beam_key(qx, qy, ox, oy)), W, &j, &d);
+    if (d2) d2[i] = d;
+    if (j < 0 || d > thr) continue;
+    if (p->use_reciprocal) {
+      /* the matched target point in the source scan's own frame: R^T (r - t), binary32, no FMA */
+      const float rx = tgt[2 * j], ry = tgt[2 * j + 1];
+      const float ex = rx - T[2], ey = ry - T[3];
+      const float bx = (T[0] * ex) + (T[1] * ey);
+      const float by = (T[0] * ey) - (T[1] * ex);
+      nn_window(rx, ry, src_t, ns, key_lower_bound(skey, ns, orc_beam_key(bx, by, ox, oy)), W, &ir, &dr);
+      if (dr > thr || ir != i) continue;
+    }
+    corr[i] = j;
+    ++K;
+  }
+  free(tkey); free(skey);
+  return K;
+}
+
 /* PCL CorrespondenceEstimation::determine[Reciprocal]Correspondences (Appendix A.3-2): for each
- * source index in order: forward NN, gate, reciprocal NN over the *current* source, require i' == i. */
-int orc_correspondences(const float *src_t, int ns, const float *tgt, int nt,
-                        const dpgicp_params *p, int fast, int32_t *corr, float *d2) {
+ * source index in order: forward NN, gate, reciprocal NN over the *current* source, require i' == i.
+ * src_orig / T (the untransformed source and the transform that produced src_t) are only read by
+ * DPGICP_SEARCH_PROJECTIVE; NULL means "src_t is the original, T = identity". */
+int orc_correspondences_ex(const float *src_t, int ns, const float *tgt, int nt, const dpgicp_params *p, int fast,
+                           const float *src_orig, const float *T, int32_t *corr, float *d2) {
   const float thr = gate_threshold(p);
   int K = 0;
   if (ns <= 0 || nt <= 0) {
     for (int i = 0; i < ns; ++i) { corr[i] = -1; if (d2) d2[i] = INFINITY; }
     return 0;
+  }
+  if (p->search == DPGICP_SEARCH_PROJECTIVE) {
+    static const float ident[4] = {1.0f, 0.0f, 0.0f, 0.0f};
+    return correspondences_projective(src_t, ns, tgt, nt, p, src_orig ? src_orig : src_t, T ? T : ident, corr, d2);
   }
   grid_t gt, gs;
   if (fast) {
@@ -261,6 +337,11 @@ int orc_correspondences(const float *src_t, int ns, const float *tgt, int nt,
     if (p->use_reciprocal) grid_free(&gs);
   }
   return K;
+}
+
+int orc_correspondences(const float *src_t, int ns, const float *tgt, int nt,
+                        const dpgicp_params *p, int fast, int32_t *corr, float *d2) {
+  return orc_correspondences_ex(src_t, ns, tgt, nt, p, fast, NULL, NULL, corr, d2);
 }
 
 /* exact fixed-point moment sums of one correspondence set */
@@ -452,7 +533,7 @@ void orc_icp(const float *src, int ns, const float *tgt, int nt, const float gue
     if (trace && trace->count < trace->capacity) {
       memcpy(trace->T_iter + 4 * trace->count, fin, sizeof(fin));
     }
-    int K = orc_correspondences(cur, ns, tgt, nt, p, fast, corr, d2);
+    int K = orc_correspondences_ex(cur, ns, tgt, nt, p, fast, src, fin, corr, d2);
     if (trace && trace->count < trace->capacity) trace->n_corr[trace->count++] = K;
     out->n_correspondences = K;
     if (K < 3) {                                   /* A.3-4: min_number_correspondences_ = 3 */
@@ -621,7 +702,7 @@ void orc_run_pair(const float *source_full, int n_source, const float *target_fu
     float *P = (float *)malloc(sizeof(float) * 2 * (size_t)(ns > 0 ? ns : 1));
     float *Q = (float *)malloc(sizeof(float) * 2 * (size_t)(ns > 0 ? ns : 1));
     orc_transform_points(T, src, ns, cur);
-    orc_correspondences(cur, ns, tgt, nt, p, fast, corr, NULL);
+    orc_correspondences_ex(cur, ns, tgt, nt, p, fast, src, T, corr, NULL);
     int k = 0;
     for (int i = 0; i < ns; ++i)
       if (corr[i] >= 0) {

@@ -53,6 +53,12 @@ void  orc_transform_points(const float T[4], const float *xy, int n, float *out_
  * fast = 0: brute force;  fast = 1: uniform-grid exact search (same answers, used for timing).  */
 int   orc_correspondences(const float *src_t, int ns, const float *tgt, int nt,
                           const dpgicp_params *p, int fast, int32_t *corr, float *d2);
+/* the same with what DPGICP_SEARCH_PROJECTIVE needs besides: the untransformed source (its beam-order keys)
+ * and T = (c, s, tx, ty), the transform that produced src_t; both NULL = src_t is the original, T = identity */
+int   orc_correspondences_ex(const float *src_t, int ns, const float *tgt, int nt, const dpgicp_params *p, int fast,
+                             const float *src_orig, const float *T, int32_t *corr, float *d2);
+/* bearing key of DPGICP_SEARCH_PROJECTIVE (include/dpgicp.h) */
+float orc_beam_key(float px, float py, float ox, float oy);
 
 /* optional per-iteration trace: T_iter[4*k] = accumulated (c,s,tx,ty) BEFORE iteration k's
  * correspondence pass (k = 0 is the guess), n_corr[k], so tests can replay any iterate.         */

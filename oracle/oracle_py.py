@@ -47,6 +47,10 @@ def lib() -> C.CDLL:
         L.orc_transform_points.argtypes = [vp, vp, C.c_int, vp]
         L.orc_correspondences.restype = C.c_int
         L.orc_correspondences.argtypes = [vp, C.c_int, vp, C.c_int, PP, C.c_int, vp, vp]
+        L.orc_correspondences_ex.restype = C.c_int
+        L.orc_correspondences_ex.argtypes = [vp, C.c_int, vp, C.c_int, PP, C.c_int, vp, vp, vp, vp]
+        L.orc_beam_key.restype = f
+        L.orc_beam_key.argtypes = [f, f, f, f]
         L.orc_icp.restype = None
         L.orc_icp.argtypes = [vp, C.c_int, vp, C.c_int, vp, PP, C.c_int, C.POINTER(Result), vp]
         L.orc_cov_censi.restype = C.c_uint32
@@ -121,12 +125,17 @@ def transform_points(T, xy) -> np.ndarray:
     return out
 
 
-def correspondences(src_t, tgt, params: Params, fast=0):
+def correspondences(src_t, tgt, params: Params, fast=0, src_orig=None, T=None):
+    """One correspondence pass.  ``src_orig`` / ``T`` (the untransformed source and the (c, s, tx, ty)
+    that produced ``src_t``) are only read by SEARCH_PROJECTIVE."""
     s, t = _f32(src_t), _f32(tgt)
     corr = np.full(s.shape[0], -1, np.int32)
     d2 = np.zeros(s.shape[0], np.float32)
-    k = lib().orc_correspondences(s.ctypes.data, s.shape[0], t.ctypes.data, t.shape[0],
-                                  C.byref(params), fast, corr.ctypes.data, d2.ctypes.data)
+    so = _f32(src_orig) if src_orig is not None else None
+    tt = _f32(T) if T is not None else None
+    k = lib().orc_correspondences_ex(s.ctypes.data, s.shape[0], t.ctypes.data, t.shape[0],
+                                     C.byref(params), fast, so.ctypes.data if so is not None else None,
+                                     tt.ctypes.data if tt is not None else None, corr.ctypes.data, d2.ctypes.data)
     return k, corr, d2
 
 

@@ -34,7 +34,7 @@ def test_header_symbols_all_exported_and_bound():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(Params) == 72 and C.sizeof(Result) == 112
+    assert C.sizeof(Params) == 80 and C.sizeof(Result) == 112
     assert Result.cov.offset == 40 and Result.mse.offset == 32 and Result.status.offset == 24
     assert _abi.RESULT_DTYPE.fields["cov"][1] == 40 and _abi.RESULT_DTYPE.itemsize == 112
 

@@ -10,7 +10,7 @@ import pytest
 
 from dpg_slam_b200 import _abi, synth
 from dpg_slam_b200._abi import (METRIC_POINT_TO_LINE, STOP_DEGENERATE, COV_CENSI_CORR, COV_CENSI_INDEXPAIR, COV_REFERENCE_LIVE, FLAG_CONVERGED,
-                                FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT, SEARCH_BRUTE, SEARCH_PRUNED, STOP_ITERATIONS,
+                                FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT, SEARCH_BRUTE, SEARCH_PRUNED, SEARCH_PROJECTIVE, STOP_ITERATIONS,
                                 STOP_MASK, STOP_NO_CORRESPONDENCES, Params)
 from dpg_slam_b200.scanmatch import DpgIcpError
 from oracle import oracle_py as O
@@ -357,6 +357,110 @@ def test_random_small_problems_bit_exact(gpu_matcher):
     with pytest.raises(DpgIcpError) as e:
         gpu_matcher.submit_pairs(src[:1], tgt[:1], guess[:1], Params.defaults(max_correspondence_distance=31.0))
     assert e.value.code == -1
+
+
+# ---- projective search (north-star extension): bit-exact against its definition in the oracle ------------------------
+@pytest.mark.parametrize("window", [3, 8, 40])
+@pytest.mark.parametrize("reciprocal", [1, 0])
+def test_projective_correspondence_sets_bit_exact_at_every_iterate(gpu_matcher, window, reciprocal):
+    wl = synth.config_loop_closure(n_pairs=3, n_scans=16, seed=33)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    p = Params.defaults(downsample_divisor=1, search=SEARCH_PROJECTIVE, projective_window=window, use_reciprocal=reciprocal,
+                        max_iterations=40)
+    for k in range(wl.n_pairs):
+        s, t = wl.src_idx[k], wl.tgt_idx[k]
+        src, tgt = pts[off[s]:off[s + 1]], pts[off[t]:off[t + 1]]
+        _, iterates, n_corr = O.icp(src, tgt, wl.guess[k], p, trace=True)
+        for it in sorted(set([0, 1, 2, len(iterates) // 2, len(iterates) - 1])):
+            T = iterates[it]
+            cur = O.transform_points(T, src)
+            kk, want, want_d2 = O.correspondences(cur, tgt, p, src_orig=src, T=T)
+            got, got_d2 = gpu_matcher.correspondences(src, tgt, T, p)
+            assert np.array_equal(got, want), (k, it)
+            m = want >= 0
+            assert np.array_equal(got_d2[m].view(np.uint32), want_d2[m].view(np.uint32)), (k, it)
+            assert int((got >= 0).sum()) == kk
+
+
+@pytest.mark.parametrize("divisor", [1, 5])
+@pytest.mark.parametrize("metric", [0, METRIC_POINT_TO_LINE])
+def test_projective_batches(gpu_matcher, divisor, metric):
+    wl = synth.config_corridor(n_pairs=64, seed=2)
+    for cov_mode in (COV_CENSI_CORR, COV_CENSI_INDEXPAIR):
+        p = Params.defaults(downsample_divisor=divisor, search=SEARCH_PROJECTIVE, cov_mode=cov_mode, metric=metric)
+        got, ref, _, _ = run_both(gpu_matcher, wl, p)
+        assert_records_match(got, ref, f"projective corridor d{divisor} m{metric} c{cov_mode}")
+    wl = synth.config_loop_closure(n_pairs=96, n_scans=40, seed=3)
+    p = Params.defaults(downsample_divisor=divisor, search=SEARCH_PROJECTIVE, cov_mode=COV_CENSI_CORR, metric=metric,
+                        projective_window=12, use_reciprocal=divisor == 1)
+    got, ref, _, _ = run_both(gpu_matcher, wl, p)
+    assert_records_match(got, ref, f"projective loop closure d{divisor} m{metric}")
+
+
+def test_projective_random_small_problems_and_sensor_origins(gpu_matcher):
+    """Ragged, empty, duplicated and lattice clouds (keys not sorted, exact ties), random windows and sensor origins."""
+    rng = np.random.default_rng(77)
+    clouds, offsets = [], [0]
+    for base_id in range(30):
+        n = int(rng.choice([0, 1, 2, 3, 5, 31, 32, 33, 64, 100, 150]))
+        kind = base_id % 3
+        if kind == 0:
+            t = np.sort(rng.uniform(0, 6, n))
+            pts = np.stack([t, 0.3 * np.sin(t)], 1)
+        elif kind == 1:
+            pts = np.stack([rng.integers(0, 8, n) * 0.25, rng.integers(0, 8, n) * 0.25], 1).astype(float)
+        else:
+            pts = rng.uniform(-3, 3, (n, 2))
+        for variant in range(2):
+            v = pts + (rng.normal(0, 0.05, 2) if variant else 0.0)
+            clouds.append(v.astype(np.float32))
+            offsets.append(offsets[-1] + len(v))
+    pts = np.concatenate(clouds).astype(np.float32)
+    off = np.array(offsets, np.int64)
+    gpu_matcher.upload_scans(pts, off)
+    n_pairs = 240
+    src = rng.integers(0, len(clouds), n_pairs).astype(np.int32)
+    tgt = (2 * (src // 2) + rng.integers(0, 2, n_pairs)).astype(np.int32)
+    guess = np.concatenate([rng.normal(0, 0.05, (n_pairs, 2)), rng.normal(0, 0.03, (n_pairs, 1))], 1).astype(np.float32)
+    for trial in range(6):
+        p = Params.defaults(downsample_divisor=int(rng.integers(1, 4)), cov_mode=int(rng.integers(0, 3)),
+                            metric=int(rng.integers(0, 2)), use_reciprocal=int(rng.integers(0, 2)), search=SEARCH_PROJECTIVE,
+                            projective_window=int(rng.choice([1, 2, 7, 33, 1024])), sensor_x=float(rng.uniform(-1, 1)),
+                            sensor_y=float(rng.uniform(-1, 1)), max_iterations=int(rng.choice([1, 4, 60])),
+                            max_correspondence_distance=float(rng.choice([0.05, 0.6, 2.5])))
+        got = gpu_matcher.submit_pairs(src, tgt, guess, p)
+        ref, _ = O.run_batch(pts, off, src, tgt, guess, p, fast=0, threads=0)
+        assert_records_match(got, ref, f"projective random trial {trial}: W {p.projective_window} div {p.downsample_divisor}")
+    for bad in (dict(projective_window=0), dict(projective_window=2000), dict(sensor_x=float("nan"))):
+        with pytest.raises(DpgIcpError) as e:
+            gpu_matcher.submit_pairs(src[:1], tgt[:1], guess[:1], Params.defaults(search=SEARCH_PROJECTIVE, **bad))
+        assert e.value.code == -1
+
+
+def test_projective_staged_chain_equals_single_stage(gpu_matcher, monkeypatch):
+    """Suspend/resume recomputes the beam-order keys from the store: any chain gives the single-stage records."""
+    from dpg_slam_b200.scanmatch import ScanMatcher
+    wl = synth.config_corridor(n_pairs=300, n_beams=721, seed=21)
+    p = Params.defaults(downsample_divisor=1, search=SEARCH_PROJECTIVE, cov_mode=COV_CENSI_CORR)
+    out = {}
+    for chain in ("16", "2,4,16", "1,4,9x4"):
+        monkeypatch.setenv("DPGICP_CHAIN", chain)
+        with ScanMatcher(0) as sm:
+            sm.upload_ranges(wl.ranges, wl.scanner)
+            out[chain] = sm.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p).copy()
+    p5 = p.copy(downsample_divisor=5, projective_window=5)
+    with ScanMatcher(0) as sm:                      # chain "1,4,9x4": resumed pairs re-gather the down-sampled originals
+        sm.upload_ranges(wl.ranges, wl.scanner)
+        chained5 = sm.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p5).copy()
+    monkeypatch.setenv("DPGICP_CHAIN", "16")
+    with ScanMatcher(0) as sm:
+        sm.upload_ranges(wl.ranges, wl.scanner)
+        assert sm.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p5).tobytes() == chained5.tobytes()
+    monkeypatch.delenv("DPGICP_CHAIN")
+    assert out["16"].tobytes() == out["2,4,16"].tobytes() == out["1,4,9x4"].tobytes()
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    ref, _ = O.run_batch(pts, off, wl.src_idx[:60], wl.tgt_idx[:60], wl.guess[:60], p, fast=0, threads=0)
+    assert_records_match(out["16"][:60], ref, "projective chain")
 
 
 # ---- the two reference call shapes -------------------------------------------------------------------------------

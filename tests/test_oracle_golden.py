@@ -11,6 +11,7 @@ from dpg_slam_b200._abi import (METRIC_POINT_TO_LINE, STOP_DEGENERATE, COV_CENSI
                                 FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT, STOP_ITERATIONS, STOP_MASK,
                                 STOP_NO_CORRESPONDENCES, Params)
 from oracle import oracle_py as O
+from dpg_slam_b200._abi import SEARCH_PROJECTIVE, SEARCH_BRUTE
 
 
 def T_from_colmajor(Tc):
@@ -331,3 +332,58 @@ def test_planar_closed_form_equals_float32_umeyama_svd():
         worst_t = max(worst_t, abs(tf[0] - res.tx), abs(tf[1] - res.ty))
         worst_r = max(worst_r, abs(th - res.theta))
     assert worst_t < 5e-6 and worst_r < 2e-6, (worst_t, worst_r)
+
+
+# ---- projective search (north-star extension; the oracle is its definition, so it is pinned by properties) ---------
+def test_beam_key_is_monotone_in_the_bearing():
+    rng = np.random.default_rng(5)
+    ang = np.sort(rng.uniform(-np.pi, np.pi, 4000))
+    r = rng.uniform(0.05, 30.0, ang.size)
+    ox, oy = 0.2, 0.0
+    keys = np.array([O.lib().orc_beam_key(np.float32(ox + rr * np.cos(a)), np.float32(oy + rr * np.sin(a)), ox, oy)
+                     for a, rr in zip(ang, r)])
+    assert np.all(keys > -2.0 - 1e-6) and np.all(keys <= 2.0 + 1e-6)
+    # monotone up to float rounding of nearly equal bearings
+    assert np.all(np.diff(keys) > -1e-5)
+    assert O.lib().orc_beam_key(0.2, 0.0, 0.2, 0.0) == 0.0                      # the origin itself
+    assert O.lib().orc_beam_key(1.2, 0.0, 0.2, 0.0) == 0.0                      # straight ahead
+    assert O.lib().orc_beam_key(0.2, 1.0, 0.2, 0.0) == 1.0                      # +90 degrees
+    assert O.lib().orc_beam_key(-1.0, 0.0, 0.2, 0.0) == 2.0                     # behind: the (-pi, pi] cut
+
+
+def test_projective_with_a_window_covering_the_scan_equals_exact_search():
+    """W >= n makes every point a candidate: the projective pass must then return what brute force returns."""
+    wl = synth.config_loop_closure(n_pairs=4, n_scans=12, n_beams=361, seed=8)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    for k in range(wl.n_pairs):
+        s, t = wl.src_idx[k], wl.tgt_idx[k]
+        src, tgt = pts[off[s]:off[s + 1]], pts[off[t]:off[t + 1]]
+        T = O.guess_matrix(wl.guess[k])
+        cur = O.transform_points(T, src)
+        for rec in (0, 1):
+            pe = Params.defaults(downsample_divisor=1, search=SEARCH_BRUTE, use_reciprocal=rec)
+            pp = Params.defaults(downsample_divisor=1, search=SEARCH_PROJECTIVE, use_reciprocal=rec, projective_window=1024)
+            ke, ce, de = O.correspondences(cur, tgt, pe)
+            kp, cp, dp = O.correspondences(cur, tgt, pp, src_orig=src, T=T)
+            assert ke == kp and np.array_equal(ce, cp)
+            assert np.array_equal(de.view(np.uint32), dp.view(np.uint32))
+    pe = Params.defaults(downsample_divisor=1, search=SEARCH_BRUTE, cov_mode=COV_CENSI_CORR)
+    pp = pe.copy(search=SEARCH_PROJECTIVE, projective_window=1024)
+    re, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, pe, fast=0)
+    rp, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, pp, fast=0)
+    assert re.tobytes() == rp.tobytes()
+
+
+def test_projective_small_window_stays_close_to_exact_search():
+    wl = synth.config_corridor(n_pairs=24, n_beams=721, seed=6)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    pe = Params.defaults(downsample_divisor=1)
+    pp = pe.copy(search=SEARCH_PROJECTIVE, projective_window=8)
+    re, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, pe, fast=1)
+    rp, _ = O.run_batch(pts, off, wl.src_idx, wl.tgt_idx, wl.guess, pp, fast=0)
+    assert np.all(rp["status"] & FLAG_CONVERGED)
+    d = np.hypot(re["tx"] - rp["tx"], re["ty"] - rp["ty"])
+    assert np.median(d) < 2e-3 and np.median(np.abs(re["theta"] - rp["theta"])) < 1e-3
+    err_e = np.hypot(re["tx"] - wl.truth[:, 0], re["ty"] - wl.truth[:, 1])
+    err_p = np.hypot(rp["tx"] - wl.truth[:, 0], rp["ty"] - wl.truth[:, 1])
+    assert np.median(err_p) < 1.5 * np.median(err_e) + 5e-3

@@ -24,7 +24,7 @@ for chain in chains:
         sm.upload_ranges(wl.ranges, wl.scanner)
         sm.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
         for div in (1, 5):
-            p = Params.defaults(downsample_divisor=div, cov_mode=COV_CENSI_CORR)
+            p = Params.defaults(downsample_divisor=div, cov_mode=COV_CENSI_CORR, search=int(os.environ.get("DPGICP_PROBE_SEARCH", "1")))
             best, med = time_run(sm, p, reps=5)
             c = sm.last_run_counters()
             key = f"st{stages}_w{warps}_c{ctas}_d{div}"
