@@ -362,22 +362,26 @@ def run_product(args):
         pass
     nominal = 148 * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
     measured = probe["mul_add_ops_per_s"] / 1e12
-    peak = measured if measured > 0 else nominal
+    packed = probe.get("mul_add_packed_ops_per_s", 0.0) / 1e12
+    # the distance loop issues its subtractions and multiplications as packed pairs (FADD2 / FMUL2): the FP32 ceiling
+    # of separately rounded operations on this GPU is the packed rate
+    peak = packed if packed > 0 else (measured if measured > 0 else nominal)
     traffic, ncu_inst = None, None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_icp_kernel_ncu.json")))
-        if WORKLOAD == "corridor":       # the capture is of this workload's launch
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_final_icp_kernel_ncu.json")))
+        if WORKLOAD == "corridor" and SEARCH == "pruned":       # the capture is of this workload's launch
             traffic = prof.get("dram_bytes_per_launch")
             ncu_inst = prof.get("instructions_executed")
     except Exception:
         pass
     alg_bytes = float(np.sum(8.0 * (ns + nt) + 20 + 112))
-    roofline = {"kernel": "dpg::icp_pairs_kernel<WARPS,PRUNED> (persistent CTAs; one step = a chain of up to 3 launches with "
-                          "growing warps per pair, timed together)",
+    roofline = {"kernel": "dpg::icp_pairs_kernel<WARPS,SEARCH,CLUSTER> (persistent CTAs; one step = a chain of up to 4 launches with "
+                          "growing warps per pair, the last as 4-CTA clusters, timed together)",
                 "bound": "fp32", "achieved": alg_tflops, "peak": peak, "unit": "TFLOP/s", "frac": alg_tflops / peak,
-                "peak_source": "measured on this GPU in this run by dpgicp_fp32_probe: separately rounded FMUL+FADD "
-                               "(the bit-exact distance loop may not use FMA); MEASURED_PEAKS.json has no FP32 figure; "
-                               f"nominal 148 SM x 128 lanes x {peaks.get('sm_max_mhz', 1965.0)} MHz = {nominal:.1f}",
+                "peak_source": "measured on this GPU in this run by dpgicp_fp32x2_probe: separately rounded FMUL2+FADD2 chains "
+                               "(packed pairs, 2 operations per issue slot; the bit-exact distance loop may not use FMA); "
+                               "MEASURED_PEAKS.json has no FP32 figure; "
+                               f"nominal scalar rate 148 SM x 128 lanes x {peaks.get('sm_max_mhz', 1965.0)} MHz = {nominal:.1f}",
                 "achieved_definition": "ALGORITHMIC brute-force flops (SURVEY 8d: I*(5*Ns*Nt+8*Ns)+14*K + 60*N_H+45*min(K,200)) / kernel time; "
                                        "the exact pruned search skips most of them, so frac can exceed 1 — see executed_*",
                 "executed_tflops": exec_tflops, "executed_frac": exec_tflops / peak,
@@ -385,7 +389,7 @@ def run_product(args):
                 "kernel_ms": k_ms, "traffic": traffic,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs"), "frac": (alg_bytes / (k_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
-                "fp32_probe_tops": {"mul_add": measured, "fma": probe["fma_ops_per_s"] / 1e12}}
+                "fp32_probe_tops": {"mul_add": measured, "mul_add_packed": packed, "fma": probe["fma_ops_per_s"] / 1e12}}
     if ncu_inst:
         # issue-slot view: warp instructions of one step (ncu capture of this same workload, profiles/) over the
         # live kernel time, against 4 schedulers x 148 SMs x SM clock
