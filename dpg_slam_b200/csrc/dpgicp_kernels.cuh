@@ -694,7 +694,7 @@ __device__ __forceinline__ long long fxp(double v) { return __double2ll_rn(__dmu
  * ---------------------------------------------------------------------------------------------- */
 /* resident CTAs per SM the register allocation is held to (DPGICP_TARGET_WARPS resident warps per SM) */
 #ifndef DPGICP_TARGET_WARPS
-#define DPGICP_TARGET_WARPS 24
+#define DPGICP_TARGET_WARPS 28
 #endif
 __host__ __device__ constexpr int min_ctas(int warps) {
   return (DPGICP_TARGET_WARPS / warps) < 1 ? 1 : (DPGICP_TARGET_WARPS / warps) > 16 ? 16 : (DPGICP_TARGET_WARPS / warps);   /* 16, 17, 32 -> 1 */
