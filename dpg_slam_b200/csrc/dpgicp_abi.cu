@@ -63,7 +63,7 @@ struct dpgicp_ctx {
   int trig_n = 0;
   float trig_min = 0.f, trig_inc = 0.f;
   DevBuf state[2], susp[2];                  /* suspended-pair state slots + pair lists, ping-pong between stages */
-  unsigned long long *d_queue = nullptr;     /* [0..4] stage queue heads, [6],[7] suspended counts, [8..15] counters, [16..23] development phase timers */
+  unsigned long long *d_queue = nullptr;     /* [0..4] stage queue heads, [6],[7] suspended counts, [8..15] counters, [16..23] development phase timers, [24..28] pairs finished per stage */
   DevBuf gather;                             /* this rank's copy of the whole batch's records (fused gather)  */
   int64_t gather_n = 0;
   int gather_world = 0, gather_rank = 0;
@@ -73,6 +73,8 @@ struct dpgicp_ctx {
   int *d_bad = nullptr;
   void *h_stage = nullptr;                   /* pinned staging for subset uploads from pageable memory */
   size_t h_stage_cap = 0;
+  double handover_factor = 2.0;              /* DPGICP_HANDOVER="f[,fc]": a stage hands over once at most f x (CTAs of the next stage) pairs are */
+  double handover_cluster = 1.0;             /* left; fc x (clusters) when the next stage runs clusters (development knob; 0 = plain queue-dry rule) */
   int force_warps = 0;
   int force_ctas_per_sm = 0;
   uint64_t launches = 0;
@@ -290,7 +292,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
       shapes[n_stages++] = {w, cs};
     }
   }
-  CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, 24 * sizeof(unsigned long long), ctx->stream));
+  CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, 32 * sizeof(unsigned long long), ctx->stream));
   int grid_prev = 0;
   if (n_stages > 1) {
     /* every stage can suspend at most one pair per CTA: size the state slots for stage 0's grid */
@@ -311,7 +313,17 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
       ks.susp_in = (const long long *)ctx->susp[(sidx - 1) & 1].p;
       ks.state_in = (const unsigned char *)ctx->state[(sidx - 1) & 1].p;
     }
+    ks.finished = ctx->d_queue + 24 + sidx;
     if (sidx + 1 < n_stages) {
+      /* hand over once the next stage could run all that is left at once (clusters: exactly; CTAs: a third more,
+       * the next stage's own queue-dry rule then takes over) */
+      int next_units = -1;
+      KernelParams kq = kp;
+      kq.resume = 1;                        /* occupancy query for the shape the next stage will really use */
+      int rcq = launch_stage(ctx, search, shapes[sidx + 1].warps, shapes[sidx + 1].csize, kq, smem, (int64_t)1 << 40, &next_units);
+      if (rcq) return rcq;
+      ks.handover = (long long)std::ceil((shapes[sidx + 1].csize > 1 ? ctx->handover_cluster : ctx->handover_factor) * (double)next_units);
+      if (ctx->handover_factor <= 0.0) ks.handover = (long long)1 << 40;      /* development: the plain queue-dry rule */
       ks.out_count = reinterpret_cast<unsigned int *>(ctx->d_queue + 6 + (sidx & 1));
       ks.susp_out = (long long *)ctx->susp[sidx & 1].p;
       ks.state_out = (unsigned char *)ctx->state[sidx & 1].p;
@@ -529,13 +541,17 @@ int dpgicp_create(int device, dpgicp_ctx **out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaMalloc((void **)&ctx->d_queue, 24 * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc((void **)&ctx->d_queue, 32 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMalloc((void **)&ctx->d_bad, sizeof(int))) != cudaSuccess) {
     delete ctx;
     return fail(nullptr, DPGICP_E_CUDA, cudaGetErrorString(e));
   }
   if (const char *w = std::getenv("DPGICP_WARPS")) ctx->force_warps = std::atoi(w);
   if (const char *c = std::getenv("DPGICP_CTAS_PER_SM")) ctx->force_ctas_per_sm = std::atoi(c);
+  if (const char *c = std::getenv("DPGICP_HANDOVER")) {
+    ctx->handover_factor = std::max(0.0, std::atof(c));
+    if (const char *q = std::strchr(c, ',')) ctx->handover_cluster = std::max(0.0, std::atof(q + 1));
+  }
   if (const char *c = std::getenv("DPGICP_STAGES")) ctx->max_stages = std::max(1, std::min(5, std::atoi(c)));
   if (const char *c = std::getenv("DPGICP_CHAIN")) {
     for (const char *q = c; *q;) {            /* e.g. "4,8,16,9x2": the last stage as clusters of 2 CTAs x 9 warps */

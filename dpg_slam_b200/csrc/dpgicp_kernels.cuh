@@ -106,6 +106,11 @@ struct KernelParams {
   long long *susp_out;
   unsigned char *state_out;
   long long slot_bytes;               /* kStateHeader + 12 * n_cap                                 */
+  /* hand-over rule of a stage that may suspend: once its queue is dry AND at most `handover` of its pairs are still
+   * running, every CTA suspends its pair at the next pass boundary.  `handover` is what the next stage can run at
+   * once: handing it more would only make pairs wait in its queue that could keep running here.            */
+  unsigned long long *finished;       /* pairs of THIS stage that ran to completion                */
+  long long handover;
   /* multi-GPU gather fused into the epilogue: with gather_world > 1 the record of local pair k also goes to
    * slot (gather_rank + k * gather_world) of EVERY rank's gather buffer — peer-mapped device memory, written
    * with plain stores over NVLink; no collective is launched                                              */
@@ -974,8 +979,11 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       parity ^= 1;
       if (tid == 0) {
         /* has this stage's queue run dry?  (read early, the L2 round trip overlaps the solve) */
-        unsigned long long qhead = 0;
-        if (P.out_count != nullptr) qhead = *reinterpret_cast<volatile unsigned long long *>(P.queue);
+        unsigned long long qhead = 0, done = 0;
+        if (P.out_count != nullptr) {
+          qhead = *reinterpret_cast<volatile unsigned long long *>(P.queue);
+          done = *reinterpret_cast<volatile unsigned long long *>(P.finished);
+        }
         const int K = (int)L.red[10];
         last_k = K;
         int st = 0;
@@ -1012,8 +1020,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
             status |= DPGICP_STOP_ABS_MSE | DPGICP_FLAG_CONVERGED; st = 1;
           } else {
             mse_prev = mse;
-            if (P.out_count != nullptr && qhead >= n_items) {
-              /* queue dry: hand this pair to the next (wider) stage */
+            if (P.out_count != nullptr && qhead >= n_items && (long long)(n_items - done) <= P.handover) {
+              /* queue dry and few enough pairs left: hand this pair to the next (wider) stage */
               st = 3;
               L.ctl[4] = (int32_t)atomicAdd(P.out_count, 1u);
             }
@@ -1171,6 +1179,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       }
       r.status = status | cov_flag;
       P.results[pair] = r;
+      if (P.out_count != nullptr) atomicAdd(P.finished, 1ull);
       if (P.gather_world > 1) {
         /* fused gather: seven 16-byte stores per peer, straight into every rank's buffer at the global slot */
         const long long slot = (long long)P.gather_rank + pair * (long long)P.gather_world;

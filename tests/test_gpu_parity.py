@@ -646,6 +646,17 @@ def test_staged_chain_equals_single_stage(gpu_matcher, monkeypatch):
             assert got.tobytes() == want.tobytes(), (stages, warps)
             c = sm.last_run_counters()
             assert c["iterations"] == int(got["iterations"].sum())
+    # the hand-over rule (a stage suspends its pairs once its queue is dry AND few enough are left for the next stage)
+    # only moves the moment of suspension
+    monkeypatch.setenv("DPGICP_STAGES", "5")
+    monkeypatch.setenv("DPGICP_WARPS", "0")
+    monkeypatch.delenv("DPGICP_CHAIN", raising=False)
+    for handover in ("0", "0.5,0.5", "1.0,3.0", "4"):
+        monkeypatch.setenv("DPGICP_HANDOVER", handover)
+        with ScanMatcher(0) as sm:
+            sm.upload_ranges(wl.ranges, wl.scanner)
+            assert sm.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p).tobytes() == want.tobytes(), handover
+    monkeypatch.delenv("DPGICP_HANDOVER")
     # down-sampled clouds take the gather path when fresh and the contiguous path when resumed
     p5 = p.copy(downsample_divisor=5)
     want5 = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p5)
