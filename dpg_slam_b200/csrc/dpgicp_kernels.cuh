@@ -360,8 +360,10 @@ struct SearchStats {
  *   (bd, bj) in: current best (the gate / a seed / for the reciprocal test the pair being tested),
  *   out: the (d2, index)-lexicographic minimum of the input and every point of the cloud.
  *   `qbox` is the bounding box of the active lanes' queries.  PRUNED = false scans every group.
+ *   POINTBOX adds a per-lane point-to-box test (and a warp vote) in front of every candidate group's scan: it pays
+ *   for the reciprocal test (21 % of its candidates are skipped), not for the forward search (12 %, measured).
  * ---------------------------------------------------------------------------------------------- */
-template <bool PRUNED>
+template <bool PRUNED, bool POINTBOX>
 __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
                                           int n_groups, float qx, float qy, bool active, float4 qbox,
                                           float &bd, int &bj, SearchStats &st, float gate) {
@@ -393,7 +395,7 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
     while (mask) {
       const int g = base + __ffs(mask) - 1;
       mask &= mask - 1;
-      if (PRUNED) {
+      if (PRUNED && POINTBOX) {
         const bool need = (lb_point_box(q2, lds128(a_boxes + g * 16)) <= bd) & active;
         if (!__any_sync(0xffffffffu, need)) continue;
       }
@@ -514,7 +516,7 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
       if (d0 <= gate) { bd = d0; bj = seed; }
     }
   }
-  nn_search<PRUNED>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, st, gate);
+  nn_search<PRUNED, false>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, st, gate);
   fwd_ok = valid && (bj != 0x7fffffff);
   j_out = bj;
   d_out = bd;
@@ -526,7 +528,7 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
     float rd = bd;
     int ri = i;
     /* dist2(r, p) == dist2(p, r) bit for bit: fl(a-b) = -fl(b-a) and the square drops the sign */
-    nn_search<PRUNED>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, rd, ri, st, gate);
+    nn_search<PRUNED, true>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, rd, ri, st, gate);
     accept = fwd_ok && (ri == i);
   }
   return accept;
