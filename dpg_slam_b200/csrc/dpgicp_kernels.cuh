@@ -22,11 +22,15 @@
  * the groups that can still beat the tile's current bound, which is seeded with the previous
  * iteration's neighbour.  Lower bounds use the same rounding sequence as the distance itself, so
  * by monotonicity of rounding they never exceed a computed distance: pruning is exact, no
- * epsilons.  SEARCH_BRUTE scans every group through the same code.
+ * epsilons.  SEARCH_BRUTE scans every group through the same code.  A group's 16 distances are
+ * packed FADD2 / FMUL2 pairs (3 issue slots per distance), their minimum a tree of three-input
+ * minima; the index of the minimum is looked up only when a lane can improve or tie.
+ * SEARCH_PROJECTIVE (north-star extension, approximate): every lane locates its query in the other
+ * scan's beam order by bisection over bearing keys and scans a window around it; defined by the oracle.
  *
  * Execution shapes: the host launches the kernel as a chain of stages with
- * growing warps per pair; a stage suspends the pairs still running when its queue runs dry (state to
- * HBM, restored bit for bit) and the last stage gives each remaining pair a thread-block cluster of
+ * growing warps per pair; a stage suspends the pairs still running once its queue is dry and few enough
+ * are left for the next stage to run at once (state to HBM, restored bit for bit) and the last stage gives each remaining pair a thread-block cluster of
  * 4 CTAs that exchange exact partial sums through distributed shared memory.  With a multi-GPU
  * gather attached, the epilogue stores each record into every rank's buffer over NVLink.
  */
