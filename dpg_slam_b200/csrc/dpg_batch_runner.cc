@@ -175,13 +175,14 @@ int main(int argc, char **argv) {
     else if (a == "--cov-mode") params.cov_mode = std::atoi(next("--cov-mode"));
     else if (a == "--metric") params.metric = std::atoi(next("--metric"));
     else if (a == "--search") params.search = std::atoi(next("--search"));
+    else if (a == "--window") params.projective_window = std::atoi(next("--window"));
     else if (a == "--same-pass-radius") r_same = (float)std::atof(next("--same-pass-radius"));
     else if (a == "--other-pass-radius") r_other = (float)std::atof(next("--other-pass-radius"));
     else if (a == "--successive-only") successive_only = true;
     else {
       std::fprintf(stderr,
                    "usage: dpg_batch_runner [--synthetic corridor|office | --log FILE] [--scans N] [--beams N] [--passes N]\n"
-                   "         [--seed S] [--divisor D] [--cov-mode 0|1|2] [--metric 0|1] [--search 0|1] [--successive-only]\n"
+                   "         [--seed S] [--divisor D] [--cov-mode 0|1|2] [--metric 0|1] [--search 0|1|2] [--window W] [--successive-only]\n"
                    "         [--same-pass-radius R] [--other-pass-radius R] [--write-log FILE] [--out FILE.csv] [--device K]\n");
       return a == "--help" ? 0 : 2;
     }

@@ -387,3 +387,43 @@ def test_projective_small_window_stays_close_to_exact_search():
     err_e = np.hypot(re["tx"] - wl.truth[:, 0], re["ty"] - wl.truth[:, 1])
     err_p = np.hypot(rp["tx"] - wl.truth[:, 0], rp["ty"] - wl.truth[:, 1])
     assert np.median(err_p) < 1.5 * np.median(err_e) + 5e-3
+
+
+def test_projective_definition_on_unsorted_and_degenerate_clouds():
+    """The bisection runs over the stored order whether or not the keys are sorted: clouds in random order, with duplicates,
+    empty or single-point clouds, and queries behind the sensor stay well defined; a window covering the cloud still equals
+    brute force, and a tiny window only ever returns indices inside the window around the bisection result."""
+    rng = np.random.default_rng(11)
+    for n_s, n_t in ((0, 5), (5, 0), (1, 1), (7, 40), (64, 33), (150, 150)):
+        src = rng.uniform(-4, 4, (n_s, 2)).astype(np.float32)
+        tgt = rng.uniform(-4, 4, (n_t, 2)).astype(np.float32)
+        if n_t > 10:
+            tgt[5] = tgt[3]                                            # duplicate point: exact tie
+        T = np.array([1, 0, 0, 0], np.float32)
+        for rec in (0, 1):
+            pe = Params.defaults(search=SEARCH_BRUTE, use_reciprocal=rec, max_correspondence_distance=2.5)
+            pw = pe.copy(search=SEARCH_PROJECTIVE, projective_window=1024, sensor_x=0.3, sensor_y=-0.2)
+            ke, ce, _ = O.correspondences(src, tgt, pe)
+            kw, cw, _ = O.correspondences(src, tgt, pw, src_orig=src, T=T)
+            assert ke == kw and np.array_equal(ce, cw), (n_s, n_t, rec)
+        if n_s and n_t:
+            W = 2
+            p2 = Params.defaults(search=SEARCH_PROJECTIVE, use_reciprocal=0, projective_window=W, sensor_x=0.3, sensor_y=-0.2,
+                                 max_correspondence_distance=30.0)
+            _, c2, _ = O.correspondences(src, tgt, p2, src_orig=src, T=T)
+            keys = np.array([O.lib().orc_beam_key(x, y, 0.3, -0.2) for x, y in tgt], np.float32)
+            for i, (x, y) in enumerate(src):
+                kq = np.float32(O.lib().orc_beam_key(x, y, 0.3, -0.2))
+                lo, hi = 0, n_t
+                while lo < hi:
+                    mid = (lo + hi) >> 1
+                    if keys[mid] < kq:
+                        lo = mid + 1
+                    else:
+                        hi = mid
+                cand = range(max(0, lo - W), min(n_t, lo + W))
+                if len(cand) == 0:
+                    assert c2[i] == -1
+                else:
+                    d = [(np.float32(x - tgt[j, 0]) ** 2 + np.float32(y - tgt[j, 1]) ** 2, j) for j in cand]
+                    assert c2[i] == min(d)[1], (n_s, n_t, i)
