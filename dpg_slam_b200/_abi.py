@@ -14,10 +14,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 # ---- constants (include/dpgicp.h) -----------------------------------------------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 METRIC_POINT_TO_POINT, METRIC_POINT_TO_LINE = 0, 1
 SEARCH_BRUTE, SEARCH_PRUNED, SEARCH_PROJECTIVE = 0, 1, 2
 COV_REFERENCE_LIVE, COV_CENSI_INDEXPAIR, COV_CENSI_CORR = 0, 1, 2
+OUTLIER_NONE, OUTLIER_TRIMMED, OUTLIER_MEDIAN = 0, 1, 2
+ENUM_REOPTIMIZE, ENUM_ONLINE = 0, 1
 STOP_MASK = 0xFF
 STOP_NONE, STOP_ITERATIONS, STOP_TRANSFORM, STOP_ABS_MSE, STOP_NO_CORRESPONDENCES, STOP_DEGENERATE = 0, 1, 2, 3, 4, 5
 FLAG_CONVERGED, FLAG_COV_SINGULAR, FLAG_EMPTY_INPUT, FLAG_FACTOR_INVALID = 0x100, 0x200, 0x400, 0x800
@@ -50,6 +52,9 @@ class Params(C.Structure):
         ("projective_window", C.c_int32),
         ("sensor_x", C.c_float),
         ("sensor_y", C.c_float),
+        ("outlier_mode", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("outlier_param", C.c_double),
     ]
 
     @classmethod
@@ -59,7 +64,8 @@ class Params(C.Structure):
                 metric=METRIC_POINT_TO_POINT, search=SEARCH_PRUNED, cov_mode=COV_REFERENCE_LIVE,
                 cov_cap=200, transformation_epsilon=5e-9, max_correspondence_distance=0.6,
                 cov_sensor_variance=0.01, laser_x_variance=0.5, laser_y_variance=0.5,
-                laser_theta_variance=0.3, projective_window=8, sensor_x=0.2, sensor_y=0.0)
+                laser_theta_variance=0.3, projective_window=8, sensor_x=0.2, sensor_y=0.0,
+                outlier_mode=OUTLIER_NONE, reserved0=0, outlier_param=0.0)
         for k, v in overrides.items():
             if not hasattr(p, k):
                 raise AttributeError(f"dpgicp_params has no field {k!r}")
@@ -98,7 +104,7 @@ FACTOR_DTYPE = np.dtype([
 ], align=True)
 
 assert C.sizeof(Result) == 112 and RESULT_DTYPE.itemsize == 112 and FACTOR_DTYPE.itemsize == 96
-assert C.sizeof(Params) == 80
+assert C.sizeof(Params) == 96
 
 EXPORTS = [
     "dpgicp_abi_version", "dpgicp_default_params", "dpgicp_create", "dpgicp_destroy",
@@ -108,6 +114,9 @@ EXPORTS = [
     "dpgicp_gather_export", "dpgicp_gather_attach", "dpgicp_gather_detach", "dpgicp_gather_fetch",
     "dpgicp_gather_device_ptr", "dpgicp_last_run_counters", "dpgicp_single_pair", "dpgicp_cov", "dpgicp_cov_pairs", "dpgicp_correspondences",
     "dpgicp_enumerate_pairs", "dpgicp_relative_guess", "dpgicp_fp32_probe", "dpgicp_fp32x2_probe",
+    "dpgicp_correspondences_seeded", "dpgicp_set_nodes", "dpgicp_enumerate_pairs_device", "dpgicp_fetch_pairs",
+    "dpgicp_convert_ranges_device", "dpgicp_gather_attach_local", "dpgicp_gather_set_root_only",
+    "dpgicp_enable_stage_timing", "dpgicp_last_run_stage_ms",
 ]
 
 _lib = None
@@ -166,6 +175,15 @@ def load_library() -> C.CDLL:
         "dpgicp_fp32x2_probe": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "dpgicp_enumerate_pairs": (C.c_int, [vp, vp, vp, i32, C.c_float, C.c_float, vp, vp,
                                               C.POINTER(i64)]),
+        "dpgicp_correspondences_seeded": (C.c_int, [vp, vp, i32, vp, i32, sz, vp, PP, vp, vp, vp, vp]),
+        "dpgicp_set_nodes": (C.c_int, [vp, vp, vp, i32]),
+        "dpgicp_enumerate_pairs_device": (C.c_int, [vp, i32, C.c_float, C.c_float, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
+        "dpgicp_fetch_pairs": (C.c_int, [vp, vp, vp, vp, i64]),
+        "dpgicp_convert_ranges_device": (C.c_int, [vp, vp, i32, i32] + [C.c_float] * 6),
+        "dpgicp_gather_attach_local": (C.c_int, [C.POINTER(vp), i32, i64, i32]),
+        "dpgicp_gather_set_root_only": (C.c_int, [vp, i32]),
+        "dpgicp_enable_stage_timing": (C.c_int, [vp, i32]),
+        "dpgicp_last_run_stage_ms": (C.c_int, [vp, C.POINTER(C.c_float * 8), C.POINTER(i32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)      # AttributeError if the symbol is not exported

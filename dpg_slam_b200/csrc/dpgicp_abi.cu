@@ -10,6 +10,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <map>
+#include <tuple>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,7 +49,17 @@ struct Batch {
   bool has_order = false;
   PairTask *h_tasks = nullptr;   /* pinned */
   size_t h_tasks_cap = 0;
+  cudaEvent_t h_tasks_free = nullptr;   /* recorded after the H2D copy out of h_tasks: the buffer may be rewritten */
   int64_t n_pairs = 0;
+  int32_t max_scan = -1;         /* device-enumerated lists: highest scan (= node) index used; -1 = validated on the host */
+};
+
+struct Nodes {                   /* pose-graph node estimates on the device (dpgicp_set_nodes) */
+  DevBuf xy, aux, pass;          /* float2 (x, y); float4 (theta, cosf(-theta), sinf(-theta), 0); int32 pass */
+  DevBuf boxes;                  /* index-order box hierarchy, all levels back to back */
+  int32_t n = 0;
+  int levels = 0;
+  int64_t level_off[8] = {0}, level_cnt[8] = {0};
 };
 
 }  // namespace
@@ -59,7 +71,20 @@ struct dpgicp_ctx {
   bool own_stream = true;
   Store store, scratch_store;
   Batch batch, scratch_batch;
-  DevBuf stage, offsets, misc, corr, trig;
+  Nodes nodes;
+  DevBuf stage, offsets, misc, corr, trig, enum_cnt;
+  /* per (kernel, warps, shared memory): resident CTAs per SM or clusters per device; per kernel: the dynamic shared
+   * memory opt-in already set — queried once, not on every run */
+  std::map<std::tuple<const void *, int, size_t>, int> occupancy;
+  std::map<const void *, size_t> smem_optin;
+  cudaEvent_t stage_ev[9] = {nullptr};
+  bool stage_timing = false;
+  int last_stages = 0;
+  void *h_pair = nullptr;                    /* pinned scratch of the single-pair call shapes */
+  size_t h_pair_cap = 0;
+  DevBuf d_pair;
+  int gather_root_only = 0;
+  bool gather_local = false;                 /* peers attached by dpgicp_gather_attach_local (no IPC mappings to close) */
   int trig_n = 0;
   float trig_min = 0.f, trig_inc = 0.f;
   DevBuf state[2], susp[2];                  /* suspended-pair state slots + pair lists, ping-pong between stages */
@@ -134,6 +159,12 @@ int check_params(dpgicp_ctx *ctx, const dpgicp_params *p) {
   if (p->cov_mode < DPGICP_COV_REFERENCE_LIVE || p->cov_mode > DPGICP_COV_CENSI_CORR)
     return fail(ctx, DPGICP_E_INVALID, "cov_mode out of range");
   if (p->cov_cap < 0) return fail(ctx, DPGICP_E_INVALID, "cov_cap must be >= 0");
+  if (p->outlier_mode != DPGICP_OUTLIER_NONE && p->outlier_mode != DPGICP_OUTLIER_TRIMMED && p->outlier_mode != DPGICP_OUTLIER_MEDIAN)
+    return fail(ctx, DPGICP_E_INVALID, "outlier_mode must be DPGICP_OUTLIER_NONE, _TRIMMED or _MEDIAN");
+  if (p->outlier_mode == DPGICP_OUTLIER_TRIMMED && !(p->outlier_param > 0.0 && p->outlier_param <= 1.0))
+    return fail(ctx, DPGICP_E_INVALID, "outlier_param (overlap ratio) must be in (0, 1] for DPGICP_OUTLIER_TRIMMED");
+  if (p->outlier_mode == DPGICP_OUTLIER_MEDIAN && !(p->outlier_param > 0.0 && std::isfinite(p->outlier_param)))
+    return fail(ctx, DPGICP_E_INVALID, "outlier_param (median factor) must be positive and finite for DPGICP_OUTLIER_MEDIAN");
   return DPGICP_OK;
 }
 
@@ -149,7 +180,13 @@ float gate_threshold(const dpgicp_params *p) {
 template <int WARPS, int SEARCH, int CSIZE>
 int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t max_items, int nw, int *grid_out) {
   auto kern = icp_pairs_kernel<WARPS, SEARCH, CSIZE>;
-  CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const void *kfn = reinterpret_cast<const void *>(kern);
+  /* the dynamic shared-memory opt-in and the occupancy of a shape do not change between runs: set / query once */
+  auto opt = ctx->smem_optin.find(kfn);
+  if (opt == ctx->smem_optin.end() || opt->second < smem) {
+    CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->smem_optin[kfn] = smem;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3((unsigned)nw * 32, 1, 1);
   cfg.dynamicSmemBytes = smem;
@@ -160,19 +197,25 @@ int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t m
   cfg.attrs = attr;
   cfg.numAttrs = CSIZE > 1 ? 1 : 0;
   int64_t units = 0;                        /* resident CTAs (CSIZE == 1) or clusters on the whole device */
-  if (CSIZE > 1) {
+  const auto key = std::make_tuple(kfn, nw, smem);
+  auto occ = ctx->occupancy.find(key);
+  if (occ != ctx->occupancy.end()) {
+    units = occ->second;
+  } else if (CSIZE > 1) {
     cfg.gridDim = dim3((unsigned)(ctx->sm_count / CSIZE) * CSIZE, 1, 1);
     int n_clusters = 0;
     CU_TRY(ctx, cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
     if (n_clusters < 1) return fail(ctx, DPGICP_E_TOOBIG, "no cluster of this shape fits the device");
     units = n_clusters;
+    ctx->occupancy[key] = n_clusters;
   } else {
     int per_sm = 0;
     CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nw * 32, smem));
     if (per_sm < 1) return fail(ctx, DPGICP_E_TOOBIG, "scan too large for one CTA's shared memory");
-    if (ctx->force_ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->force_ctas_per_sm);
     units = (int64_t)ctx->sm_count * per_sm;
+    ctx->occupancy[key] = (int)units;
   }
+  if (CSIZE == 1 && ctx->force_ctas_per_sm > 0) units = std::min<int64_t>(units, (int64_t)ctx->sm_count * ctx->force_ctas_per_sm);
   /* persistent grid: a whole number of resident CTAs per SM (or clusters), never more than work items */
   if (units > max_items) units = max_items;
   if (units < 1) units = 1;
@@ -221,7 +264,7 @@ int balanced_warps(int tiles, int target, int csize = 1) {
 }
 
 int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_params *p, int32_t *corr_out,
-               float *corr_d2) {
+               float *corr_d2, const int32_t *corr_seed = nullptr, int32_t *corr_nn_out = nullptr) {
   NvtxRange range("dpgicp: ICP + covariance stage chain");
   const int div = p->downsample_divisor;
   int n_max = (st.max_count + div - 1) / div;
@@ -252,18 +295,24 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   kp.live[0] = p->laser_x_variance; kp.live[1] = p->laser_y_variance; kp.live[2] = p->laser_theta_variance;
   kp.corr_out = corr_out;
   kp.corr_d2_out = corr_d2;
+  kp.corr_seed = corr_seed;
+  kp.corr_nn_out = corr_nn_out;
+  kp.outlier_mode = p->outlier_mode;
+  kp.outlier_param = p->outlier_param;
   kp.slot_bytes = (long long)kStateHeader + 12ll * n_cap;
   if (ctx->gather_world > 1 && corr_out == nullptr && &b == &ctx->batch) {
     if ((b.n_pairs - 1) * (int64_t)ctx->gather_world + ctx->gather_rank >= ctx->gather_n)
       return fail(ctx, DPGICP_E_STATE, "the attached gather buffers are too small for this shard");
     kp.gather_world = ctx->gather_world;
     kp.gather_rank = ctx->gather_rank;
+    kp.gather_fanout = ctx->gather_root_only ? 1 : ctx->gather_world;
     for (int g = 0; g < ctx->gather_world; ++g) kp.gather_peer[g] = (dpgicp_result *)ctx->gather_peer[g];
   }
   kp.proj_window = p->projective_window;
   kp.sensor_x = p->sensor_x;
   kp.sensor_y = p->sensor_y;
-  const size_t smem = smem_bytes(n_cap, p->search == DPGICP_SEARCH_PROJECTIVE);
+  const bool trim = p->outlier_mode != DPGICP_OUTLIER_NONE;
+  const size_t smem = smem_bytes(n_cap, p->search == DPGICP_SEARCH_PROJECTIVE, trim);
   const int search = p->search;
 
   /* stage widths (warps per pair): narrow CTAs for the bulk of the batch, wider ones for the pairs
@@ -275,11 +324,11 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   /* 34 tiles (1081 beams) -> 4, 7, 12 warps per CTA, then clusters of 4 CTAs x 9 warps (one tile per warp on four
    * SMs) for the last pairs: measured per-pass latency of one pair 28.7 / 17.9 / 11.4 / 6.3 us */
   StageShape targets[5] = {{w0, 1}, {std::min(16, 2 * w0), 1}, {16, 1}, {16, 4}, {16, 1}};
-  int n_targets = tiles >= 16 ? 4 : 3;
+  int n_targets = (tiles >= 16 && !trim) ? 4 : 3;      /* the rejector's block-wide select does not span a cluster */
   if (!ctx->chain.empty()) {
     n_targets = 0;
     for (size_t k = 0; k < ctx->chain.size() && n_targets < 5; ++k)
-      targets[n_targets++] = {ctx->chain[k], ctx->chain_cluster[k]};
+      targets[n_targets++] = {ctx->chain[k], trim ? 1 : ctx->chain_cluster[k]};
   }
   StageShape shapes[5] = {{balanced_warps(tiles, targets[0].warps), 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}};
   int n_stages = 1;
@@ -294,6 +343,8 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   }
   CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, 32 * sizeof(unsigned long long), ctx->stream));
   int grid_prev = 0;
+  const bool timing = ctx->stage_timing && corr_out == nullptr;
+  if (timing) { ctx->last_stages = n_stages; CU_TRY(ctx, cudaEventRecord(ctx->stage_ev[0], ctx->stream)); }
   if (n_stages > 1) {
     /* every stage can suspend at most one pair per CTA: size the state slots for stage 0's grid */
     int g0 = -1;
@@ -335,6 +386,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
     int rc = launch_stage(ctx, search, shapes[sidx].warps, shapes[sidx].csize, ks, smem, max_items, &grid);
     if (rc) return rc;
     grid_prev = grid;
+    if (timing) CU_TRY(ctx, cudaEventRecord(ctx->stage_ev[sidx + 1], ctx->stream));
   }
   return DPGICP_OK;
 }
@@ -397,6 +449,10 @@ int set_pairs_into(dpgicp_ctx *ctx, const Store &st, Batch &b, const int32_t *sr
   if (n < 0 || (n > 0 && (!src || !tgt || (!guess && !T_direct))))
     return fail(ctx, DPGICP_E_INVALID, "bad pair arguments");
   if (st.n_scans <= 0 && n > 0) return fail(ctx, DPGICP_E_STATE, "no scans uploaded");
+  /* dpgicp_run is asynchronous: the previous list's H2D copy out of the pinned staging buffer may still be queued
+   * behind a running kernel; wait for it before the buffer is rewritten (or freed) */
+  if (b.h_tasks_free) CU_TRY(ctx, cudaEventSynchronize(b.h_tasks_free));
+  else CU_TRY(ctx, cudaEventCreateWithFlags(&b.h_tasks_free, cudaEventDisableTiming));
   if ((size_t)n > b.h_tasks_cap) {
     if (b.h_tasks) cudaFreeHost(b.h_tasks);
     b.h_tasks = nullptr; b.h_tasks_cap = 0;
@@ -430,8 +486,10 @@ int set_pairs_into(dpgicp_ctx *ctx, const Store &st, Batch &b, const int32_t *sr
   if ((rc = reserve(ctx, b.results, sizeof(dpgicp_result) * (size_t)std::max<int64_t>(n, 1)))) return rc;
   if (n > 0)
     CU_TRY(ctx, cudaMemcpyAsync(b.tasks.p, b.h_tasks, sizeof(PairTask) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaEventRecord(b.h_tasks_free, ctx->stream));
   b.n_pairs = n;
   b.has_order = false;
+  b.max_scan = -1;
   return DPGICP_OK;
 }
 
@@ -457,10 +515,11 @@ int ensure_trig(dpgicp_ctx *ctx, int n_beams, float angle_min, float angle_inc) 
 /* close the peer mappings of the fused gather */
 int gather_close(dpgicp_ctx *ctx) {
   for (int g = 0; g < ctx->gather_world; ++g) {
-    if (g != ctx->gather_rank && ctx->gather_peer[g]) cudaIpcCloseMemHandle(ctx->gather_peer[g]);
+    if (!ctx->gather_local && g != ctx->gather_rank && ctx->gather_peer[g]) cudaIpcCloseMemHandle(ctx->gather_peer[g]);
     ctx->gather_peer[g] = nullptr;
   }
   ctx->gather_world = 0;
+  ctx->gather_local = false;
   return DPGICP_OK;
 }
 
@@ -483,6 +542,152 @@ int two_cloud_store(dpgicp_ctx *ctx, const void *a, int na, const void *b, int n
   pa.insert(pa.end(), pb.begin(), pb.end());
   const int64_t off[3] = {0, na, (int64_t)na + nb};
   return upload_scans_into(ctx, ctx->scratch_store, pa.data(), 8, off, 2);
+}
+
+
+/* node estimates -> device, plus the index-order box hierarchy the enumeration walks */
+int set_nodes_impl(dpgicp_ctx *ctx, const float *pose, const int32_t *pass, int32_t n, bool pose_is_xy) {
+  Nodes &N = ctx->nodes;
+  N.n = 0;
+  if (n == 0) return DPGICP_OK;
+  std::vector<float> xy((size_t)n * 2), aux((size_t)n * 4);
+  const int stride = pose_is_xy ? 2 : 3;
+  for (int32_t k = 0; k < n; ++k) {
+    const float x = pose[(size_t)stride * k], y = pose[(size_t)stride * k + 1], th = pose_is_xy ? 0.0f : pose[(size_t)stride * k + 2];
+    if (!std::isfinite(x) || !std::isfinite(y) || !std::isfinite(th))
+      return fail(ctx, DPGICP_E_RANGE, "non-finite node estimate at node " + std::to_string(k));
+    xy[2 * (size_t)k] = x; xy[2 * (size_t)k + 1] = y;
+    const float ang = -th;                            /* Eigen::Rotation2Df(-theta_1), math_utils.cc:28 */
+    aux[4 * (size_t)k] = th; aux[4 * (size_t)k + 1] = cosf(ang); aux[4 * (size_t)k + 2] = sinf(ang); aux[4 * (size_t)k + 3] = 0.f;
+  }
+  int rc;
+  if ((rc = reserve(ctx, N.xy, sizeof(float) * 2 * (size_t)n))) return rc;
+  if ((rc = reserve(ctx, N.aux, sizeof(float) * 4 * (size_t)n))) return rc;
+  if ((rc = reserve(ctx, N.pass, sizeof(int32_t) * (size_t)n))) return rc;
+  /* levels: L = 1 boxes of 32 nodes, L + 1 boxes of 32 level-L boxes, until one warp can test the top level at once */
+  N.levels = 0;
+  int64_t total = 0, cnt = n;
+  do {
+    cnt = (cnt + kEnumFan - 1) / kEnumFan;
+    if (N.levels >= kEnumMaxLevels) return fail(ctx, DPGICP_E_TOOBIG, "too many nodes");
+    N.level_off[N.levels] = total; N.level_cnt[N.levels] = cnt;
+    total += cnt; ++N.levels;
+  } while (cnt > kEnumFan);
+  if ((rc = reserve(ctx, N.boxes, sizeof(NodeBox) * (size_t)total))) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(N.xy.p, xy.data(), sizeof(float) * 2 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(N.aux.p, aux.data(), sizeof(float) * 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(N.pass.p, pass, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  NodeBox *bx = (NodeBox *)N.boxes.p;
+  {
+    const int nb = (int)N.level_cnt[0], blocks = (nb + 3) / 4;
+    node_boxes_leaf_kernel<<<blocks, 128, 0, ctx->stream>>>((const float2 *)N.xy.p, (const int32_t *)N.pass.p, n, bx, nb);
+    ctx->launches++;
+  }
+  for (int L = 1; L < N.levels; ++L) {
+    const int nb = (int)N.level_cnt[L], blocks = (nb + 3) / 4;
+    node_boxes_up_kernel<<<blocks, 128, 0, ctx->stream>>>(bx + N.level_off[L - 1], (int)N.level_cnt[L - 1], bx + N.level_off[L], nb);
+    ctx->launches++;
+  }
+  CU_TRY(ctx, cudaGetLastError());
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));         /* the host staging vectors go out of scope */
+  N.n = n;
+  return DPGICP_OK;
+}
+
+/* the caller's pair list of `mode` built on the device into batch b (this shard's part); host learns the counts */
+int enumerate_into(dpgicp_ctx *ctx, Batch &b, int mode, float r_same, float r_other, int rank, int world,
+                   int64_t *n_total, int64_t *n_local) {
+  Nodes &N = ctx->nodes;
+  if (n_total) *n_total = 0;
+  if (n_local) *n_local = 0;
+  b.n_pairs = 0; b.has_order = false; b.max_scan = -1;
+  if (N.n < 2) return DPGICP_OK;
+  const int n = N.n;
+  const int n_chunks = mode == DPGICP_ENUM_ONLINE ? std::max(1, (n - 3 + 31) / 32) : n;
+  int rc;
+  if ((rc = reserve(ctx, ctx->enum_cnt, sizeof(unsigned long long) * ((size_t)n_chunks + 1) + 8 + sizeof(long long) * 4096))) return rc;
+  EnumParams E;
+  std::memset(&E, 0, sizeof(E));
+  E.xy = (const float2 *)N.xy.p; E.pass = (const int32_t *)N.pass.p; E.aux = (const float4 *)N.aux.p;
+  E.boxes = (const NodeBox *)N.boxes.p;
+  for (int L = 0; L < N.levels; ++L) { E.level_off[L] = N.level_off[L]; E.level_cnt[L] = (int32_t)N.level_cnt[L]; }
+  E.levels = N.levels; E.n = n; E.r_same = r_same; E.r_other = r_other;
+  E.cnt = (unsigned long long *)ctx->enum_cnt.p;
+  E.amb_count = (unsigned int *)(E.cnt + n_chunks + 1);
+  E.amb_list = (long long *)(E.cnt + n_chunks + 2);
+  E.amb_cap = 4096;
+  E.rank = rank; E.world = world;
+  const int blocks = (n_chunks + 3) / 4;
+  if (mode == DPGICP_ENUM_ONLINE) enumerate_online_kernel<false><<<blocks, 128, 0, ctx->stream>>>(E, n_chunks);
+  else enumerate_reopt_kernel<false><<<blocks, 128, 0, ctx->stream>>>(E);
+  scan_u64_kernel<<<1, 1024, 0, ctx->stream>>>(E.cnt, n_chunks);
+  ctx->launches += 2;
+  CU_TRY(ctx, cudaGetLastError());
+  unsigned long long total = 0;
+  CU_TRY(ctx, cudaMemcpyAsync(&total, E.cnt + n_chunks, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaMemsetAsync(E.amb_count, 0, sizeof(unsigned int), ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const int64_t local = (int64_t)total > rank ? ((int64_t)total - rank + world - 1) / world : 0;
+  if (n_total) *n_total = (int64_t)total;
+  if (n_local) *n_local = local;
+  if ((rc = reserve(ctx, b.tasks, sizeof(PairTask) * (size_t)std::max<int64_t>(local, 1)))) return rc;
+  if ((rc = reserve(ctx, b.results, sizeof(dpgicp_result) * (size_t)std::max<int64_t>(local, 1)))) return rc;
+  E.tasks = (PairTask *)b.tasks.p;
+  if (mode == DPGICP_ENUM_ONLINE) enumerate_online_kernel<true><<<blocks, 128, 0, ctx->stream>>>(E, n_chunks);
+  else enumerate_reopt_kernel<true><<<blocks, 128, 0, ctx->stream>>>(E);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  /* pairs whose cos/sin of the guess angle sit within a few binary64 ulps of a binary32 rounding boundary (about one
+   * in 10^7): the device's libm and the host's are not guaranteed to round them alike, so the host — whose libm defines
+   * the guess matrix everywhere else (set_pairs) — re-derives them */
+  unsigned int amb = 0;
+  CU_TRY(ctx, cudaMemcpyAsync(&amb, E.amb_count, sizeof(amb), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (amb > (unsigned)E.amb_cap) return fail(ctx, DPGICP_E_STATE, "too many guess angles at a rounding boundary (internal limit)");
+  if (amb > 0) {
+    std::vector<long long> slots(amb);
+    CU_TRY(ctx, cudaMemcpyAsync(slots.data(), E.amb_list, sizeof(long long) * amb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (long long slot : slots) {
+      PairTask t;
+      CU_TRY(ctx, cudaMemcpyAsync(&t, (PairTask *)b.tasks.p + slot, sizeof(t), cudaMemcpyDeviceToHost, ctx->stream));
+      CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      float th[2];
+      CU_TRY(ctx, cudaMemcpyAsync(&th[0], (const float4 *)N.aux.p + t.tgt, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      CU_TRY(ctx, cudaMemcpyAsync(&th[1], (const float4 *)N.aux.p + t.src, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      double d = (double)(float)(th[1] - th[0]);
+      d -= (M_PI * 2.0) * rint(d / (M_PI * 2.0));
+      const float g2 = (float)d;
+      t.c = (float)std::cos((double)g2); t.s = (float)std::sin((double)g2);
+      CU_TRY(ctx, cudaMemcpyAsync((PairTask *)b.tasks.p + slot, &t, sizeof(t), cudaMemcpyHostToDevice, ctx->stream));
+      CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  b.n_pairs = local;
+  b.max_scan = n - 1;
+  return DPGICP_OK;
+}
+
+/* the pair list of a batch back on the host */
+int fetch_pairs_from(dpgicp_ctx *ctx, const Batch &b, int32_t *src, int32_t *tgt, float *T, int64_t n) {
+  if (n < 0 || n > b.n_pairs) return fail(ctx, DPGICP_E_INVALID, "bad fetch arguments");
+  if (n == 0) return DPGICP_OK;
+  int rc;
+  if ((rc = reserve(ctx, ctx->stage, (size_t)n * 24 + 64))) return rc;
+  int32_t *d_src = (int32_t *)ctx->stage.p, *d_tgt = d_src + n;
+  float4 *d_T = (float4 *)((char *)ctx->stage.p + (((size_t)n * 8 + 15) & ~(size_t)15));
+  const int threads = 256;
+  const long long blocks = (n + threads - 1) / threads;
+  unpack_tasks_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>((const PairTask *)b.tasks.p, (long long)n, src ? d_src : nullptr,
+                                                                   tgt ? d_tgt : nullptr, T ? d_T : nullptr);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  if (src) CU_TRY(ctx, cudaMemcpyAsync(src, d_src, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (tgt) CU_TRY(ctx, cudaMemcpyAsync(tgt, d_tgt, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (T) CU_TRY(ctx, cudaMemcpyAsync(T, d_T, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
 }
 
 }  // namespace
@@ -546,6 +751,8 @@ int dpgicp_create(int device, dpgicp_ctx **out) {
     delete ctx;
     return fail(nullptr, DPGICP_E_CUDA, cudaGetErrorString(e));
   }
+  for (cudaEvent_t &ev : ctx->stage_ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) { delete ctx; return fail(nullptr, DPGICP_E_CUDA, cudaGetErrorString(e)); }
   if (const char *w = std::getenv("DPGICP_WARPS")) ctx->force_warps = std::atoi(w);
   if (const char *c = std::getenv("DPGICP_CTAS_PER_SM")) ctx->force_ctas_per_sm = std::atoi(c);
   if (const char *c = std::getenv("DPGICP_HANDOVER")) {
@@ -574,7 +781,12 @@ void dpgicp_destroy(dpgicp_ctx *ctx) {
   for (Batch *b : {&ctx->batch, &ctx->scratch_batch}) {
     release(b->tasks); release(b->results); release(b->order);
     if (b->h_tasks) cudaFreeHost(b->h_tasks);
+    if (b->h_tasks_free) cudaEventDestroy(b->h_tasks_free);
   }
+  for (cudaEvent_t e : ctx->stage_ev) if (e) cudaEventDestroy(e);
+  release(ctx->nodes.xy); release(ctx->nodes.aux); release(ctx->nodes.pass); release(ctx->nodes.boxes);
+  release(ctx->enum_cnt); release(ctx->d_pair);
+  if (ctx->h_pair) cudaFreeHost(ctx->h_pair);
   gather_close(ctx);
   release(ctx->gather);
   release(ctx->stage); release(ctx->offsets); release(ctx->misc); release(ctx->corr); release(ctx->trig);
@@ -744,6 +956,8 @@ int dpgicp_set_pair_cost_hints(dpgicp_ctx *ctx, const float *hints, int64_t n) {
   if (!hints) { b.has_order = false; return DPGICP_OK; }
   if (n != b.n_pairs) return fail(ctx, DPGICP_E_INVALID, "hint count differs from the pair list");
   if (n == 0) return DPGICP_OK;
+  for (int64_t k = 0; k < n; ++k)       /* a NaN would break the strict weak ordering the sorts below rely on */
+    if (!std::isfinite(hints[k])) return fail(ctx, DPGICP_E_RANGE, "non-finite cost hint at pair " + std::to_string(k));
   /* Only the quarter of the pairs with the largest hints is moved to the front (most expensive first); the rest keep
    * their input order.  A full descending sort would put every pair predicted cheap at the very end — exactly where
    * a mispredicted long alignment hurts most; this way a misprediction starts at an arbitrary time, as without
@@ -772,6 +986,8 @@ int dpgicp_run(dpgicp_ctx *ctx, const dpgicp_params *params) {
   if (ctx->batch.n_pairs == 0) return DPGICP_OK;               /* an empty batch is valid and does nothing */
   if (ctx->batch.n_pairs < 0) return fail(ctx, DPGICP_E_STATE, "no pair list set");
   if (ctx->store.n_scans <= 0) return fail(ctx, DPGICP_E_STATE, "no scans uploaded");
+  if (ctx->batch.max_scan >= ctx->store.n_scans)
+    return fail(ctx, DPGICP_E_STATE, "the enumerated pair list refers to nodes without a scan in the store (node k owns scan k)");
   return launch_icp(ctx, ctx->store, ctx->batch, params, nullptr, nullptr);
 }
 
@@ -811,7 +1027,8 @@ int dpgicp_gather_export(dpgicp_ctx *ctx, int64_t n_global, unsigned char handle
   static_assert(sizeof(cudaIpcMemHandle_t) == DPGICP_IPC_HANDLE_BYTES, "IPC handle size");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  gather_close(ctx);
+  if (ctx->gather_world > 0)
+    return fail(ctx, DPGICP_E_STATE, "gather buffers are attached (peers may still store into this one): dpgicp_gather_detach on every rank first");
   /* a dedicated cudaMalloc allocation (IPC handles cover whole allocations) */
   release(ctx->gather);
   int rc;
@@ -845,6 +1062,49 @@ int dpgicp_gather_attach(dpgicp_ctx *ctx, const unsigned char *handles, int32_t 
   }
   ctx->gather_world = world;
   ctx->gather_rank = rank;
+  return DPGICP_OK;
+}
+
+int dpgicp_gather_set_root_only(dpgicp_ctx *ctx, int32_t root_only) {
+  if (!ctx) return DPGICP_E_INVALID;
+  ctx->gather_root_only = root_only != 0;
+  return DPGICP_OK;
+}
+
+int dpgicp_gather_attach_local(dpgicp_ctx **ctxs, int32_t world, int64_t n_global, int32_t root_only) {
+  if (!ctxs || world < 1 || world > DPGICP_MAX_GATHER_RANKS || n_global < 0) return DPGICP_E_INVALID;
+  for (int r = 0; r < world; ++r) if (!ctxs[r]) return DPGICP_E_INVALID;
+  /* every rank's buffer (rank 0's only when root_only), then peer access between the devices, then the pointers */
+  for (int r = 0; r < world; ++r) {
+    dpgicp_ctx *ctx = ctxs[r];
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    gather_close(ctx);
+    release(ctx->gather);
+    const int64_t want = (root_only && r > 0) ? 1 : std::max<int64_t>(n_global, 1);
+    int rc;
+    if ((rc = reserve(ctx, ctx->gather, sizeof(dpgicp_result) * (size_t)want))) return rc;
+    CU_TRY(ctx, cudaMemsetAsync(ctx->gather.p, 0, ctx->gather.cap, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->gather_n = n_global;
+    for (int g = 0; g < world; ++g) {
+      if (ctxs[g]->device == ctx->device) continue;
+      int can = 0;
+      CU_TRY(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[g]->device));
+      if (!can) return fail(ctx, DPGICP_E_CUDA, "no peer access from device " + std::to_string(ctx->device) + " to device " + std::to_string(ctxs[g]->device));
+      cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[g]->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return fail(ctx, DPGICP_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    }
+  }
+  for (int r = 0; r < world; ++r) {
+    dpgicp_ctx *ctx = ctxs[r];
+    for (int g = 0; g < world; ++g) ctx->gather_peer[g] = ctxs[g]->gather.p;
+    ctx->gather_world = world;
+    ctx->gather_rank = r;
+    ctx->gather_root_only = root_only != 0;
+    ctx->gather_local = true;
+  }
   return DPGICP_OK;
 }
 
@@ -940,30 +1200,44 @@ int dpgicp_single_pair(dpgicp_ctx *ctx, const void *source, int32_t n_source, co
   return DPGICP_OK;
 }
 
-int dpgicp_correspondences(dpgicp_ctx *ctx, const void *source, int32_t n_source, const void *target,
-                           int32_t n_target, size_t stride, const float T[4], const dpgicp_params *params,
-                           int32_t *corr_tgt, float *corr_d2) {
+int dpgicp_correspondences_seeded(dpgicp_ctx *ctx, const void *source, int32_t n_source, const void *target,
+                                  int32_t n_target, size_t stride, const float T[4], const dpgicp_params *params,
+                                  const int32_t *prev_nn, int32_t *corr_tgt, float *corr_d2, int32_t *nn_out) {
   if (!ctx) return DPGICP_E_INVALID;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   int rc = check_params(ctx, params);
   if (rc) return rc;
   if (!T || (n_source > 0 && (!corr_tgt || !corr_d2))) return fail(ctx, DPGICP_E_INVALID, "T/corr outputs NULL");
+  if (prev_nn)
+    for (int32_t i = 0; i < n_source; ++i)
+      if (prev_nn[i] < -1 || prev_nn[i] >= n_target) return fail(ctx, DPGICP_E_INVALID, "prev_nn out of range at point " + std::to_string(i));
   if ((rc = two_cloud_store(ctx, source, n_source, target, n_target, stride))) return rc;
   const int32_t s = 0, t = 1;
   if ((rc = set_pairs_into(ctx, ctx->scratch_store, ctx->scratch_batch, &s, &t, nullptr, T, 1))) return rc;
   const size_t n = (size_t)std::max(n_source, 1);
-  if ((rc = reserve(ctx, ctx->corr, n * 8))) return rc;
+  if ((rc = reserve(ctx, ctx->corr, n * 16))) return rc;
   dpgicp_params p = *params;
   p.downsample_divisor = 1;          /* the clouds given here are the ICP clouds */
   int32_t *d_corr = (int32_t *)ctx->corr.p;
   float *d_d2 = (float *)((char *)ctx->corr.p + n * 4);
-  if ((rc = launch_icp(ctx, ctx->scratch_store, ctx->scratch_batch, &p, d_corr, d_d2))) return rc;
+  int32_t *d_seed = (int32_t *)((char *)ctx->corr.p + n * 8);
+  int32_t *d_nn = (int32_t *)((char *)ctx->corr.p + n * 12);
+  if (prev_nn && n_source > 0)
+    CU_TRY(ctx, cudaMemcpyAsync(d_seed, prev_nn, sizeof(int32_t) * (size_t)n_source, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launch_icp(ctx, ctx->scratch_store, ctx->scratch_batch, &p, d_corr, d_d2, prev_nn ? d_seed : nullptr, nn_out ? d_nn : nullptr))) return rc;
   if (n_source > 0) {
     CU_TRY(ctx, cudaMemcpyAsync(corr_tgt, d_corr, sizeof(int32_t) * (size_t)n_source, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(corr_d2, d_d2, sizeof(float) * (size_t)n_source, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nn_out) CU_TRY(ctx, cudaMemcpyAsync(nn_out, d_nn, sizeof(int32_t) * (size_t)n_source, cudaMemcpyDeviceToHost, ctx->stream));
   }
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return DPGICP_OK;
+}
+
+int dpgicp_correspondences(dpgicp_ctx *ctx, const void *source, int32_t n_source, const void *target,
+                           int32_t n_target, size_t stride, const float T[4], const dpgicp_params *params,
+                           int32_t *corr_tgt, float *corr_d2) {
+  return dpgicp_correspondences_seeded(ctx, source, n_source, target, n_target, stride, T, params, nullptr, corr_tgt, corr_d2, nullptr);
 }
 
 int dpgicp_cov(dpgicp_ctx *ctx, const void *data_pi, int32_t n_data, const void *model_qi, int32_t n_model,
@@ -1072,37 +1346,98 @@ int dpgicp_enumerate_pairs(dpgicp_ctx *ctx, const float *node_xy, const int32_t 
   const int64_t capacity = *n_pairs;
   *n_pairs = 0;
   if (n_nodes < 2) return DPGICP_OK;
-  const size_t n = (size_t)n_nodes;
+  /* the device enumeration with the list copied out: positions only (theta = 0), scratch batch */
   int rc;
-  if ((rc = reserve(ctx, ctx->misc, n * (8 + 4 + 8) + 64))) return rc;
-  char *base = (char *)ctx->misc.p;
-  float2 *d_xy = (float2 *)base;
-  unsigned long long *d_cnt = (unsigned long long *)(base + n * 8);
-  int32_t *d_pass = (int32_t *)(base + n * 16);
-  CU_TRY(ctx, cudaMemcpyAsync(d_xy, node_xy, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU_TRY(ctx, cudaMemcpyAsync(d_pass, node_pass, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-  const int threads = 128, blocks = (n_nodes + threads - 1) / threads;
-  enumerate_count_kernel<<<blocks, threads, 0, ctx->stream>>>(d_xy, d_pass, n_nodes, r_same, r_other, d_cnt);
-  ctx->launches++;
-  CU_TRY(ctx, cudaGetLastError());
-  std::vector<unsigned long long> cnt(n);
-  CU_TRY(ctx, cudaMemcpyAsync(cnt.data(), d_cnt, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  unsigned long long total = 0;
-  for (size_t i = 0; i < n; ++i) { const unsigned long long c = cnt[i]; cnt[i] = total; total += c; }
-  *n_pairs = (int64_t)total;
-  if ((int64_t)total > capacity || (total > 0 && (!src || !tgt)))
+  if ((rc = set_nodes_impl(ctx, node_xy, node_pass, n_nodes, true))) return rc;
+  int64_t total = 0, local = 0;
+  rc = enumerate_into(ctx, ctx->scratch_batch, DPGICP_ENUM_REOPTIMIZE, r_same, r_other, 0, 1, &total, &local);
+  ctx->nodes.n = 0;                          /* positions only: not a node table dpgicp_enumerate_pairs_device may use */
+  if (rc) return rc;
+  *n_pairs = total;
+  if (total > capacity || (total > 0 && (!src || !tgt))) {
+    ctx->scratch_batch.n_pairs = 0;
     return fail(ctx, DPGICP_E_TOOBIG, "pair capacity too small; required count returned in *n_pairs");
-  if (total == 0) return DPGICP_OK;
-  if ((rc = reserve(ctx, ctx->stage, (size_t)total * 8 + 16))) return rc;
-  int32_t *d_src = (int32_t *)ctx->stage.p, *d_tgt = d_src + total;
-  CU_TRY(ctx, cudaMemcpyAsync(d_cnt, cnt.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
-  enumerate_fill_kernel<<<blocks, threads, 0, ctx->stream>>>(d_xy, d_pass, n_nodes, r_same, r_other, d_cnt, d_src, d_tgt);
+  }
+  rc = fetch_pairs_from(ctx, ctx->scratch_batch, src, tgt, nullptr, total);
+  ctx->scratch_batch.n_pairs = 0;
+  return rc;
+}
+
+int dpgicp_set_nodes(dpgicp_ctx *ctx, const float *pose, const int32_t *pass, int32_t n) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n < 0 || (n > 0 && (!pose || !pass))) return fail(ctx, DPGICP_E_INVALID, "bad node arguments");
+  return set_nodes_impl(ctx, pose, pass, n, false);
+}
+
+int dpgicp_enumerate_pairs_device(dpgicp_ctx *ctx, int32_t mode, float r_same, float r_other, int32_t rank, int32_t world,
+                                  int64_t *n_total, int64_t *n_local) {
+  if (!ctx) return DPGICP_E_INVALID;
+  NvtxRange range("dpgicp: enumerate pairs (device)");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (mode != DPGICP_ENUM_REOPTIMIZE && mode != DPGICP_ENUM_ONLINE) return fail(ctx, DPGICP_E_INVALID, "mode must be DPGICP_ENUM_REOPTIMIZE or DPGICP_ENUM_ONLINE");
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, DPGICP_E_INVALID, "bad shard arguments");
+  if (!(r_same >= 0.0f) || !(r_other >= 0.0f)) return fail(ctx, DPGICP_E_INVALID, "radii must be >= 0");
+  if (ctx->nodes.n <= 0) {
+    if (n_total) *n_total = 0;
+    if (n_local) *n_local = 0;
+    ctx->batch.n_pairs = 0;
+    return DPGICP_OK;
+  }
+  return enumerate_into(ctx, ctx->batch, mode, r_same, r_other, rank, world, n_total, n_local);
+}
+
+int dpgicp_fetch_pairs(dpgicp_ctx *ctx, int32_t *src, int32_t *tgt, float *T, int64_t n) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  return fetch_pairs_from(ctx, ctx->batch, src, tgt, T, n);
+}
+
+int dpgicp_convert_ranges_device(dpgicp_ctx *ctx, const float *d_ranges, int32_t n_scans, int32_t n_beams, float angle_min,
+                                 float angle_max, float range_max, float lx, float ly, float ltheta) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n_scans < 0 || n_beams < 2 || (n_scans > 0 && !d_ranges)) return fail(ctx, DPGICP_E_INVALID, "bad range-scan arguments");
+  if (n_beams > DPGICP_MAX_POINTS) return fail(ctx, DPGICP_E_TOOBIG, "n_beams exceeds DPGICP_MAX_POINTS");
+  Store &st = ctx->store;
+  ctx->batch.n_pairs = 0;
+  const int pitch = (n_beams + 1) & ~1;
+  int rc;
+  if ((rc = reserve(ctx, st.rows, sizeof(float2) * (size_t)pitch * (size_t)std::max(n_scans, 1)))) return rc;
+  if ((rc = reserve(ctx, st.count, sizeof(int32_t) * (size_t)std::max(n_scans, 1)))) return rc;
+  st.pitch = pitch;
+  st.n_scans = 0;
+  if (n_scans == 0) { st.max_count = 0; st.h_count.clear(); return DPGICP_OK; }
+  CU_TRY(ctx, cudaMemsetAsync(ctx->d_bad, 0, sizeof(int), ctx->stream));
+  const float angle_inc = (float)(((double)(float)(angle_max - angle_min)) / ((double)n_beams - 1.0));
+  const float lc = cosf(ltheta), ls = sinf(ltheta);
+  const int threads = 128, warps_per_block = threads / 32;
+  const int blocks = (n_scans + warps_per_block - 1) / warps_per_block;
+  if ((rc = ensure_trig(ctx, n_beams, angle_min, angle_inc))) return rc;
+  ranges_to_rows_kernel<<<blocks, threads, 0, ctx->stream>>>(d_ranges, nullptr, n_scans, n_beams, (const double2 *)ctx->trig.p,
+                                                            range_max, lx, ly, lc, ls, pitch, (float2 *)st.rows.p,
+                                                            (int32_t *)st.count.p, ctx->d_bad);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
-  CU_TRY(ctx, cudaMemcpyAsync(src, d_src, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(ctx, cudaMemcpyAsync(tgt, d_tgt, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return finish_store(ctx, st, n_scans);
+}
+
+int dpgicp_enable_stage_timing(dpgicp_ctx *ctx, int32_t on) {
+  if (!ctx) return DPGICP_E_INVALID;
+  ctx->stage_timing = on != 0;
+  ctx->last_stages = 0;
+  return DPGICP_OK;
+}
+
+int dpgicp_last_run_stage_ms(dpgicp_ctx *ctx, float stage_ms[8], int32_t *n_stages) {
+  if (!ctx || !stage_ms || !n_stages) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  *n_stages = 0;
+  for (int k = 0; k < 8; ++k) stage_ms[k] = 0.f;
+  if (!ctx->stage_timing || ctx->last_stages <= 0) return fail(ctx, DPGICP_E_STATE, "stage timing is off (dpgicp_enable_stage_timing) or nothing has run");
+  CU_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[ctx->last_stages]));
+  for (int k = 0; k < ctx->last_stages; ++k) CU_TRY(ctx, cudaEventElapsedTime(&stage_ms[k], ctx->stage_ev[k], ctx->stage_ev[k + 1]));
+  *n_stages = ctx->last_stages;
   return DPGICP_OK;
 }
 

@@ -98,6 +98,11 @@ struct KernelParams {
   /* dpgicp_correspondences hook: when corr_out != nullptr the kernel runs ONE pass for pair 0    */
   int32_t *corr_out;
   float *corr_d2_out;
+  const int32_t *corr_seed;       /* ... seeded with these forward neighbours (nullptr: none)    */
+  int32_t *corr_nn_out;           /* ... and reports this pass's gated forward neighbours (may be nullptr) */
+  /* outlier rejection (DPGICP_OUTLIER_*; never combined with a cluster stage by the host) */
+  int32_t outlier_mode;
+  double outlier_param;
   /* staged execution (see icp_pairs_kernel): work items of stage > 0 are the pairs the previous
    * stage suspended when its queue ran dry; they are resumed by wider CTAs                        */
   const long long *order;             /* fresh stage only: item k is pair order[k] (nullptr = identity): callers that
@@ -120,6 +125,7 @@ struct KernelParams {
    * with plain stores over NVLink; no collective is launched                                              */
   dpgicp_result *gather_peer[DPGICP_MAX_GATHER_RANKS];
   int32_t gather_world, gather_rank;
+  int32_t gather_fanout;              /* buffers written: gather_world (every rank's) or 1 (rank 0's only)        */
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -281,15 +287,16 @@ struct SmemLayout {
   float *fin;       /* 4: accumulated transform (c, s, tx, ty), read by the projective reciprocal test   */
   float *tkey;      /* projective search only: n_cap beam-order keys of the target ...                    */
   float *skey;      /* ... and of the untransformed source                                                */
+  float *ad2;       /* outlier rejection only: n_cap squared distances of the accepted pairs (+inf: none)  */
 };
 
-__host__ __device__ inline size_t smem_bytes(int n_cap, bool projective) {
+__host__ __device__ inline size_t smem_bytes(int n_cap, bool projective, bool trim) {
   const int g = n_cap / kGroup, t = n_cap / kTile;
   return (size_t)n_cap * (8 + 8 + 4) + (size_t)g * (16 + 16) + (size_t)t * (16 + 4) + 48 * 8 + kMaxWarps * 12 * 8 + 16 + 32 +
-         16 + 64 + 16 + (projective ? (size_t)n_cap * 8 : 0);
+         16 + 64 + 16 + (projective ? (size_t)n_cap * 8 : 0) + (trim ? (size_t)n_cap * 4 : 0);
 }
 
-__device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap) {
+__device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap, bool projective) {
   const int g = n_cap / kGroup, t = n_cap / kTile;
   SmemLayout L;
   size_t o = 0;
@@ -306,8 +313,10 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap) {
   L.step = (float *)(base + o);   o += 16;
   L.ctl = (int32_t *)(base + o);  o += 32;
   L.fin = (float *)(base + o);    o += 16;
-  L.tkey = (float *)(base + o);   o += (size_t)n_cap * 4;     /* present only when launched for the projective search */
-  L.skey = (float *)(base + o);
+  L.tkey = (float *)(base + o);                               /* present only when launched for the projective search */
+  L.skey = L.tkey + n_cap;
+  if (projective) o += (size_t)n_cap * 8;
+  L.ad2 = (float *)(base + o);                                /* present only when launched with outlier rejection    */
   return L;
 }
 
@@ -359,23 +368,32 @@ struct SearchStats {
 #endif
 };
 
+/* largest binary32 strictly below a squared distance (d2 >= +0): "gd <= below(bd)" is "gd < bd" in one compare */
+__device__ __forceinline__ float below(float d2) {
+  return d2 > 0.0f ? __int_as_float(__float_as_int(d2) - 1) : -1.0f;
+}
+
 /* ------------------------------------------------------------------------------------------------
- * Exact nearest neighbour of one query per lane over a grouped cloud in shared memory.
- *   (bd, bj) in: current best (the gate / a seed / for the reciprocal test the pair being tested),
- *   out: the (d2, index)-lexicographic minimum of the input and every point of the cloud.
+ * Exact forward nearest neighbour of one query per lane over a grouped cloud in shared memory.
+ *   (bd, bj) in: the gate with bj = INT_MAX, or — seeded = true — the neighbour of the previous pass and its distance;
+ *   out: the minimum squared distance and its index under the tie rule of include/dpgicp.h: a seeded lane keeps its
+ *   seed unless a point is STRICTLY closer; otherwise the lowest index among the minimisers wins.
+ *   Each lane carries thr = the largest group minimum that still changes its answer (bd, or the float just below bd
+ *   for a lane still on its seed), so one compare decides whether the (d2, index) bookkeeping — first index attaining
+ *   the group minimum, 2 instructions per point — has to run at all; with seeds that are still the nearest neighbours
+ *   (the steady state of ICP) it never does.
  *   `qbox` is the bounding box of the active lanes' queries.  PRUNED = false scans every group.
- *   POINTBOX adds a per-lane point-to-box test (and a warp vote) in front of every candidate group's scan: it pays
- *   for the reciprocal test (21 % of its candidates are skipped), not for the forward search (12 %, measured).
  * ---------------------------------------------------------------------------------------------- */
-template <bool PRUNED, bool POINTBOX>
-__device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
-                                          int n_groups, float qx, float qy, bool active, float4 qbox,
-                                          float &bd, int &bj, SearchStats &st, float gate) {
+template <bool PRUNED>
+__device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
+                                           int n_groups, float qx, float qy, bool active, float4 qbox,
+                                           float &bd, int &bj, bool seeded, SearchStats &st, float gate) {
   const int lane = threadIdx.x & 31;
   const uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
   const f32x2 q2 = pack2(qx, qy);
+  float thr = active ? (seeded ? below(bd) : bd) : -1.0f;
   float bmax = 0.0f;
-  if (PRUNED) bmax = warp_max(active ? bd : -1.0f);
+  if (PRUNED) bmax = warp_max(thr);
 #ifdef DPGICP_STATS
   st.searches++;
   if (bmax >= gate) st.loose++;
@@ -399,14 +417,8 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
     while (mask) {
       const int g = base + __ffs(mask) - 1;
       mask &= mask - 1;
-      if (PRUNED && POINTBOX) {
-        const bool need = (lb_point_box(q2, lds128(a_boxes + g * 16)) <= bd) & active;
-        if (!__any_sync(0xffffffffu, need)) continue;
-      }
       ++st.scans;
       const uint32_t a_grp = a_cloud + g * (kGroup * 8);
-      /* all kGroup distances with packed arithmetic (3 instructions each), their minimum by a tree of
-       * three-input minima; the (d2, index) bookkeeping runs only when some lane can improve or tie */
       float dd[kGroup];
       float gd = __int_as_float(0x7f800000);
 #define DPG_SCAN2(T)                                                                                  \
@@ -419,7 +431,7 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
       DPG_SCAN2(0) DPG_SCAN2(1) DPG_SCAN2(2) DPG_SCAN2(3) DPG_SCAN2(4) DPG_SCAN2(5) DPG_SCAN2(6) DPG_SCAN2(7)
       DPG_SCAN2(8) DPG_SCAN2(9) DPG_SCAN2(10) DPG_SCAN2(11) DPG_SCAN2(12) DPG_SCAN2(13) DPG_SCAN2(14) DPG_SCAN2(15)
 #undef DPG_SCAN2
-      if (!__any_sync(0xffffffffu, active && gd <= bd)) continue;
+      if (!__any_sync(0xffffffffu, gd <= thr)) continue;
 #ifdef DPGICP_STATS
       st.updates++;
 #endif
@@ -428,9 +440,67 @@ __device__ __forceinline__ void nn_search(const float2 *__restrict__ cloud, cons
       for (int t = kGroup - 2; t >= 0; --t)
         if (dd[t] == gd) gj = t;
       const int j = g * kGroup + gj;
-      if (gd < bd || (gd == bd && j < bj)) { bd = gd; bj = j; }
+      /* groups come in ascending order: a tie with an earlier group's point (j > bj) never wins */
+      if (gd <= thr && (gd < bd || j < bj)) { bd = gd; bj = j; thr = gd; }
     }
   }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Reciprocal test as an emptiness query: is any point of the cloud STRICTLY closer to this lane's query than bd?
+ * (the asker wins exact ties, include/dpgicp.h).  No indices are tracked; a lane that has found a closer point stops
+ * asking for scans.  A per-lane point-to-box test and a warp vote in front of every candidate group's scan skip the
+ * groups no lane can use (21 % of the candidates, measured).
+ * ---------------------------------------------------------------------------------------------- */
+template <bool PRUNED>
+__device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
+                                                 int n_groups, float qx, float qy, bool active, float4 qbox, float bd,
+                                                 SearchStats &st) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
+  const f32x2 q2 = pack2(qx, qy);
+  float thr = active ? below(bd) : -1.0f;               /* -1: this lane needs nothing (any more) */
+  float bmax = 0.0f;
+  if (PRUNED) bmax = warp_max(thr);
+#ifdef DPGICP_STATS
+  st.searches++;
+#endif
+  for (int base = 0; base < n_groups; base += 32) {
+    unsigned mask;
+    if (PRUNED) {
+      const int g = base + lane;
+      const bool cand = (lb_box_box(qbox, lds128(a_boxes + g * 16)) <= bmax) & (g < n_groups);
+      mask = __ballot_sync(0xffffffffu, cand);
+      ++st.tests;
+#ifdef DPGICP_STATS
+      st.cands += __popc(mask);
+#endif
+    } else {
+      const int rem = n_groups - base;
+      mask = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+    }
+    while (mask) {
+      const int g = base + __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (PRUNED) {
+        const bool need = lb_point_box(q2, lds128(a_boxes + g * 16)) <= thr;
+        if (!__any_sync(0xffffffffu, need)) continue;
+      }
+      ++st.scans;
+      const uint32_t a_grp = a_cloud + g * (kGroup * 8);
+      float gd = __int_as_float(0x7f800000);
+#define DPG_SCAN2(T)                                                                                  \
+      if (2 * (T) < kGroup) {                                                                         \
+        const float4 p = lds128_off<16 * (T)>(a_grp);                                                 \
+        gd = fminf(fminf(gd, dist2_packed(q2, pack2(p.x, p.y))), dist2_packed(q2, pack2(p.z, p.w)));  \
+      }
+      DPG_SCAN2(0) DPG_SCAN2(1) DPG_SCAN2(2) DPG_SCAN2(3) DPG_SCAN2(4) DPG_SCAN2(5) DPG_SCAN2(6) DPG_SCAN2(7)
+      DPG_SCAN2(8) DPG_SCAN2(9) DPG_SCAN2(10) DPG_SCAN2(11) DPG_SCAN2(12) DPG_SCAN2(13) DPG_SCAN2(14) DPG_SCAN2(15)
+#undef DPG_SCAN2
+      if (gd <= thr) thr = -1.0f;                       /* a strictly closer point: this lane is done */
+    }
+  }
+  return active && thr < 0.0f;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -512,15 +582,15 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
   q = L.src[i];
   float bd = gate;
   int bj = 0x7fffffff;
-  if (PRUNED) {
-    const int seed = valid ? L.nn[i] : -1;
-    if (seed >= 0) {
-      const float2 p = L.tgt[seed];
-      const float d0 = dist2(q.x, q.y, p.x, p.y);
-      if (d0 <= gate) { bd = d0; bj = seed; }
-    }
+  /* the previous pass's neighbour seeds the bound and is the tie preference (brute force and pruned search alike) */
+  bool seeded = false;
+  const int seed = valid ? L.nn[i] : -1;
+  if (seed >= 0) {
+    const float2 p = L.tgt[seed];
+    const float d0 = dist2(q.x, q.y, p.x, p.y);
+    if (d0 <= gate) { bd = d0; bj = seed; seeded = true; }
   }
-  nn_search<PRUNED, false>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, st, gate);
+  nn_forward<PRUNED>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, seeded, st, gate);
   fwd_ok = valid && (bj != 0x7fffffff);
   j_out = bj;
   d_out = bd;
@@ -529,11 +599,10 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
     float2 r = make_float2(0.f, 0.f);
     if (fwd_ok) r = L.tgt[bj];
     const float4 rbox = warp_box(r, fwd_ok);
-    float rd = bd;
-    int ri = i;
-    /* dist2(r, p) == dist2(p, r) bit for bit: fl(a-b) = -fl(b-a) and the square drops the sign */
-    nn_search<PRUNED, true>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, rd, ri, st, gate);
-    accept = fwd_ok && (ri == i);
+    /* dist2(r, p) == dist2(p, r) bit for bit: fl(a-b) = -fl(b-a) and the square drops the sign, so source point i
+     * itself is at exactly bd from r and "strictly closer than bd" is well defined */
+    const bool closer = nn_closer_exists<PRUNED>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, bd, st);
+    accept = fwd_ok && !closer;
   }
   return accept;
 }
@@ -691,6 +760,149 @@ __device__ __forceinline__ bool solve_p2l(const long long *red, float st[4]) {
 __device__ __forceinline__ long long fxp(double v) { return __double2ll_rn(__dmul_rn(v, kScaleProd)); }
 
 /* ------------------------------------------------------------------------------------------------
+ * Moment sums of one accepted pair (q = current source point, target j, d = squared distance): m[0..8] are the
+ * nine exact fixed-point sums of the metric, m[9] = sum d2 (2^40).  Mirrors oracle/dpg_oracle.c accumulate_moments /
+ * accumulate_normal_eq term for term.
+ * ---------------------------------------------------------------------------------------------- */
+template <typename KP>
+__device__ __forceinline__ void accumulate_pair(const SmemLayout &L, const KP &P, float2 q, int j, float d, int nt,
+                                                long long (&m)[10], int &m_k) {
+  const float2 t = L.tgt[j];
+  const double px = q.x, py = q.y, qx = t.x, qy = t.y;
+  if (P.metric == DPGICP_METRIC_POINT_TO_LINE) {
+    /* line through the matched target point and its closer beam neighbour (oracle:
+     * accumulate_normal_eq); m0..m5 = A (11,12,13,22,23,33), m6..m8 = sum J^T r */
+    int j2 = -1;
+    float best = __int_as_float(0x7f800000);
+    if (j - 1 >= 0) { const float2 a = L.tgt[j - 1]; best = dist2(q.x, q.y, a.x, a.y); j2 = j - 1; }
+    if (j + 1 < nt) {
+      const float2 a = L.tgt[j + 1];
+      const float dn = dist2(q.x, q.y, a.x, a.y);
+      if (dn < best) { best = dn; j2 = j + 1; }
+    }
+    bool line = false;
+    double nx = 0.0, ny = 0.0;
+    if (j2 >= 0) {
+      const float2 a = L.tgt[j2];
+      const float seg = dist2(a.x, a.y, t.x, t.y);
+      if (seg > 0.0f && seg <= P.gate) {
+        const double tx = __dsub_rn((double)a.x, qx), ty = __dsub_rn((double)a.y, qy);
+        const double len = __dsqrt_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)));
+        nx = __ddiv_rn(-ty, len);
+        ny = __ddiv_rn(tx, len);
+        line = true;
+      }
+    }
+    const double ex = __dsub_rn(px, qx), ey = __dsub_rn(py, qy);
+    if (line) {
+      const double r = __dadd_rn(__dmul_rn(nx, ex), __dmul_rn(ny, ey));
+      const double j3 = __dsub_rn(__dmul_rn(ny, px), __dmul_rn(nx, py));
+      m[0] += fxp(__dmul_rn(nx, nx)); m[1] += fxp(__dmul_rn(nx, ny)); m[2] += fxp(__dmul_rn(nx, j3));
+      m[3] += fxp(__dmul_rn(ny, ny)); m[4] += fxp(__dmul_rn(ny, j3)); m[5] += fxp(__dmul_rn(j3, j3));
+      m[6] += fxp(__dmul_rn(nx, r)); m[7] += fxp(__dmul_rn(ny, r)); m[8] += fxp(__dmul_rn(j3, r));
+    } else {
+      m[0] += fxp(1.0); m[2] += fxp(-py);
+      m[3] += fxp(1.0); m[4] += fxp(px);
+      m[5] += fxp(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
+      m[6] += fxp(ex); m[7] += fxp(ey);
+      m[8] += fxp(__dsub_rn(__dmul_rn(px, ey), __dmul_rn(py, ex)));
+    }
+  } else {
+    /* point-to-point moments: sums of p, q (2^32) and of the four products (2^28) */
+    m[0] += __double2ll_rn(__dmul_rn(px, kScaleLin));
+    m[1] += __double2ll_rn(__dmul_rn(py, kScaleLin));
+    m[2] += __double2ll_rn(__dmul_rn(qx, kScaleLin));
+    m[3] += __double2ll_rn(__dmul_rn(qy, kScaleLin));
+    m[4] += fxp(__dmul_rn(px, qx));
+    m[5] += fxp(__dmul_rn(px, qy));
+    m[6] += fxp(__dmul_rn(py, qx));
+    m[7] += fxp(__dmul_rn(py, qy));
+  }
+  m[9] += __double2ll_rn(__dmul_rn((double)d, kScaleD2));
+  m_k += 1;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Outlier rejection threshold tau (include/dpgicp.h DPGICP_OUTLIER_*; oracle: orc_outlier_threshold) over the accepted
+ * squared distances L.ad2[0 .. n_pad) (+inf = not accepted).  Exact block-wide radix select: four rounds of 8 bits over
+ * the binary32 patterns (d2 >= +0, so the patterns order like the values), a 256-bin histogram in shared memory per
+ * round.  Every thread of the CTA calls it between two __syncthreads-separated phases; all get the same tau
+ * (+inf when fewer than 3 pairs were accepted: the pass stops anyway).  Scratch: L.dpart (free between the passes'
+ * reductions) and L.ctl[5..7].
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ float select_tau(const SmemLayout &L, int n_pad, int mode, double param) {
+  const float inf = __int_as_float(0x7f800000);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  int *hist = reinterpret_cast<int *>(L.dpart);
+  int *sel = L.ctl + 5;
+  if (tid == 0) sel[0] = 0;
+  __syncthreads();
+  int c = 0;
+  for (int k = tid; k < n_pad; k += nthreads) c += (L.ad2[k] < inf) ? 1 : 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0 && c) atomicAdd(&sel[0], c);
+  __syncthreads();
+  const int K = sel[0];
+  if (K < 3) return inf;
+  int r;
+  if (mode == DPGICP_OUTLIER_TRIMMED) {
+    int keep = (int)floor(__dmul_rn(param, (double)K));
+    keep = keep < 3 ? 3 : keep;
+    keep = keep > K ? K : keep;
+    r = keep - 1;
+  } else {
+    r = K / 2;
+  }
+  uint32_t prefix = 0;
+  for (int round = 0; round < 4; ++round) {
+    const int shift = 24 - 8 * round;
+    for (int k = tid; k < 256; k += nthreads) hist[k] = 0;
+    __syncthreads();
+    const uint32_t himask = round == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int k = tid; k < n_pad; k += nthreads) {
+      const uint32_t key = __float_as_uint(L.ad2[k]);
+      if (key < 0x7f800000u && (key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int h[8], tot = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { h[u] = hist[lane * 8 + u]; tot += h[u]; }
+      int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int excl = incl - tot;
+      const bool mine = r >= excl && r < incl;         /* exactly one lane: the bins hold K > r keys in all */
+      int bin = 0, before = 0;
+      if (mine) {
+        int acc = excl;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (r >= acc && r < acc + h[u]) { bin = lane * 8 + u; before = acc; }
+          acc += h[u];
+        }
+      }
+      const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+      bin = __shfl_sync(0xffffffffu, bin, src);
+      before = __shfl_sync(0xffffffffu, before, src);
+      if (lane == 0) { sel[1] = bin; sel[2] = before; }
+    }
+    __syncthreads();
+    prefix |= (uint32_t)sel[1] << shift;
+    r -= sel[2];
+  }
+  const float stat = __uint_as_float(prefix);
+  if (mode == DPGICP_OUTLIER_TRIMMED) return stat;
+  const double lim = __dmul_rn((double)stat, param);
+  float tau = __double2float_rn(lim);
+  if ((double)tau > lim) tau = __uint_as_float(__float_as_uint(tau) - 1u);   /* nextafterf(tau, -inf), tau > 0 here */
+  return tau;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * The persistent ICP + covariance kernel.
  *
  * Staged execution.  ICP iteration counts are heavy-tailed (corridor workload: median 37, p99 174,
@@ -732,7 +944,7 @@ __device__ __forceinline__ T *peer_smem(T *p, int rank) {
 template <int WARPS, int SEARCH, int CSIZE>
 __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(const KernelParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const SmemLayout L = carve(smem_raw, P.n_cap);
+  const SmemLayout L = carve(smem_raw, P.n_cap, SEARCH == DPGICP_SEARCH_PROJECTIVE);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nw = blockDim.x >> 5;            /* warps of this CTA: <= WARPS (and <= 16), chosen by the host so
                                               * that the pair's tiles divide evenly among them                 */
@@ -743,9 +955,13 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
   const int div = P.divisor;
   constexpr int GPT = kTile / kGroup;        /* groups per tile */
   uint32_t mbar_phase = 0;
+  const bool trim = (CSIZE == 1) && P.outlier_mode != DPGICP_OUTLIER_NONE;   /* the host never combines it with clusters */
 
   if (tid == 0) mbar_init(L.mbar, 1);
   __syncthreads();
+  /* a CTA may address a peer's shared memory only once every CTA of the cluster has started: one cluster barrier
+   * before the first work fetch (which stores the item into the peers' control words) */
+  if constexpr (CSIZE > 1) cooperative_groups::this_cluster().sync();
 
   SearchStats stats;
   unsigned long long c_iters = 0, c_corr = 0;
@@ -818,7 +1034,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       }
       if (!P.resume) {
         if (k < ns) { p = xform(task.c, task.s, task.tx, task.ty, p); L.src[k] = p; }
-        L.nn[k] = -1;
+        L.nn[k] = (P.corr_seed != nullptr && k < ns) ? P.corr_seed[k] : -1;
       }
       if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
     }
@@ -839,10 +1055,18 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         float2 q; int j; float d; bool fwd;
         const bool acc = match_any<SEARCH>(L, P, tile, ns, nt, gs, gt, q, j, d, fwd, stats);
         const int i = tile * kTile + lane;
+        if (trim) L.ad2[i] = acc ? d : __int_as_float(0x7f800000);
         if (i < ns) {
           P.corr_out[i] = acc ? j : -1;
           P.corr_d2_out[i] = fwd ? d : __int_as_float(0x7f800000);
+          if (P.corr_nn_out != nullptr) P.corr_nn_out[i] = fwd ? j : -1;
         }
+      }
+      if (trim) {
+        __syncthreads();
+        const float tau = select_tau(L, ts * kTile, P.outlier_mode, P.outlier_param);
+        for (int i = tid; i < ns; i += nthreads)
+          if (!(L.ad2[i] <= tau)) P.corr_out[i] = -1;
       }
       continue;
     }
@@ -870,81 +1094,38 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
 #define PH_MARK(k) do { } while (0)
 #endif
     for (;;) {
-      long long m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, m6 = 0, m7 = 0, m8 = 0, m_d2 = 0;
+      long long m[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       int m_k = 0;
       for (int tile = tile0; tile < ts; tile += tile_stride) {
         float2 q; int j; float d; bool fwd;
         const bool acc = match_any<SEARCH>(L, P, tile, ns, nt, gs, gt, q, j, d, fwd, stats);
         const int i = tile * kTile + lane;
-        if (i < ns) L.nn[i] = fwd ? j : -1;           /* seed of the next pass */
-        if (acc) {
-          const float2 t = L.tgt[j];
-          const double px = q.x, py = q.y, qx = t.x, qy = t.y;
-          if (P.metric == DPGICP_METRIC_POINT_TO_LINE) {
-            /* line through the matched target point and its closer beam neighbour (oracle:
-             * accumulate_normal_eq); m0..m5 = A (11,12,13,22,23,33), m6..m8 = sum J^T r */
-            int j2 = -1;
-            float best = __int_as_float(0x7f800000);
-            if (j - 1 >= 0) { const float2 a = L.tgt[j - 1]; best = dist2(q.x, q.y, a.x, a.y); j2 = j - 1; }
-            if (j + 1 < nt) {
-              const float2 a = L.tgt[j + 1];
-              const float dn = dist2(q.x, q.y, a.x, a.y);
-              if (dn < best) { best = dn; j2 = j + 1; }
-            }
-            bool line = false;
-            double nx = 0.0, ny = 0.0;
-            if (j2 >= 0) {
-              const float2 a = L.tgt[j2];
-              const float seg = dist2(a.x, a.y, t.x, t.y);
-              if (seg > 0.0f && seg <= P.gate) {
-                const double tx = __dsub_rn((double)a.x, qx), ty = __dsub_rn((double)a.y, qy);
-                const double len = __dsqrt_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)));
-                nx = __ddiv_rn(-ty, len);
-                ny = __ddiv_rn(tx, len);
-                line = true;
-              }
-            }
-            const double ex = __dsub_rn(px, qx), ey = __dsub_rn(py, qy);
-            if (line) {
-              const double r = __dadd_rn(__dmul_rn(nx, ex), __dmul_rn(ny, ey));
-              const double j3 = __dsub_rn(__dmul_rn(ny, px), __dmul_rn(nx, py));
-              m0 += fxp(__dmul_rn(nx, nx)); m1 += fxp(__dmul_rn(nx, ny)); m2 += fxp(__dmul_rn(nx, j3));
-              m3 += fxp(__dmul_rn(ny, ny)); m4 += fxp(__dmul_rn(ny, j3)); m5 += fxp(__dmul_rn(j3, j3));
-              m6 += fxp(__dmul_rn(nx, r)); m7 += fxp(__dmul_rn(ny, r)); m8 += fxp(__dmul_rn(j3, r));
-            } else {
-              m0 += fxp(1.0); m2 += fxp(-py);
-              m3 += fxp(1.0); m4 += fxp(px);
-              m5 += fxp(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
-              m6 += fxp(ex); m7 += fxp(ey);
-              m8 += fxp(__dsub_rn(__dmul_rn(px, ey), __dmul_rn(py, ex)));
-            }
-          } else {
-            /* point-to-point moments: sums of p, q (2^32) and of the four products (2^28) */
-            m0 += __double2ll_rn(__dmul_rn(px, kScaleLin));
-            m1 += __double2ll_rn(__dmul_rn(py, kScaleLin));
-            m2 += __double2ll_rn(__dmul_rn(qx, kScaleLin));
-            m3 += __double2ll_rn(__dmul_rn(qy, kScaleLin));
-            m4 += fxp(__dmul_rn(px, qx));
-            m5 += fxp(__dmul_rn(px, qy));
-            m6 += fxp(__dmul_rn(py, qx));
-            m7 += fxp(__dmul_rn(py, qy));
-          }
-          m_d2 += __double2ll_rn(__dmul_rn((double)d, kScaleD2));
-          m_k += 1;
+        if (i < ns) L.nn[i] = fwd ? j : -1;           /* seed (and tie preference) of the next pass */
+        if (trim) L.ad2[i] = acc ? d : __int_as_float(0x7f800000);
+        else if (acc) accumulate_pair(L, P, q, j, d, nt, m, m_k);
+      }
+      if (trim) {
+        /* outlier rejection: threshold from the accepted distances of the whole pair, then the sums over the kept */
+        __syncthreads();
+        const float tau = select_tau(L, ts * kTile, P.outlier_mode, P.outlier_param);
+        for (int tile = tile0; tile < ts; tile += tile_stride) {
+          const int i = tile * kTile + lane;
+          const float d = L.ad2[i];
+          if (d < __int_as_float(0x7f800000) && d <= tau) accumulate_pair(L, P, L.src[i], L.nn[i], d, nt, m, m_k);
         }
       }
       PH_MARK(0);                                     /* own tiles */
       /* exact integer reduction: warp shuffles, then one shared atomic per warp and value */
-      m0 = warp_sum_i64(m0); m1 = warp_sum_i64(m1); m2 = warp_sum_i64(m2);
-      m3 = warp_sum_i64(m3); m4 = warp_sum_i64(m4); m5 = warp_sum_i64(m5);
-      m6 = warp_sum_i64(m6); m7 = warp_sum_i64(m7); m8 = warp_sum_i64(m8); m_d2 = warp_sum_i64(m_d2);
+#pragma unroll
+      for (int k = 0; k < 10; ++k) m[k] = warp_sum_i64(m[k]);
       m_k = __reduce_add_sync(0xffffffffu, m_k);
       if (lane == 0) {
         /* per-warp partials in shared memory (plain stores; a 64-bit shared atomicAdd is a CAS spin loop);
          * the slots alias L.dpart, which is only used by the covariance after the pass loop */
         long long *w = reinterpret_cast<long long *>(L.dpart) + (parity * 16 + warp) * 12;
-        w[0] = m0; w[1] = m1; w[2] = m2; w[3] = m3; w[4] = m4; w[5] = m5; w[6] = m6; w[7] = m7; w[8] = m8;
-        w[9] = m_d2; w[10] = (long long)m_k;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) w[k] = m[k];
+        w[10] = (long long)m_k;
       }
       PH_MARK(1);                                     /* warp reduction + partial slots */
       __syncthreads();                                /* all warps of this CTA have stored */
@@ -1118,7 +1299,20 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           const unsigned bal = __ballot_sync(0xffffffffu, ok);
           const int i = tile * kTile + lane;
           if (i < ns) L.nn[i] = ok ? j : -1;
+          if (trim) L.ad2[i] = ok ? d : __int_as_float(0x7f800000);
           if (lane == 0) L.tcnt[tile] = __popc(bal);
+        }
+        if (trim) {
+          /* the same rejector as in the iterations, on the correspondences at the final pose */
+          __syncthreads();
+          const float tau = select_tau(L, ts * kTile, P.outlier_mode, P.outlier_param);
+          for (int tile = tile0; tile < ts; tile += tile_stride) {
+            const int i = tile * kTile + lane;
+            const bool keep = L.ad2[i] <= tau && L.ad2[i] < __int_as_float(0x7f800000);
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (i < ns && !keep) L.nn[i] = -1;
+            if (lane == 0) L.tcnt[tile] = __popc(bal);
+          }
         }
         pair_sync<CSIZE>();
         n_cov = ns;
@@ -1169,7 +1363,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
     }
 
     if (tid == 0 && crank == 0) {
-      dpgicp_result r;
+      static_assert(sizeof(dpgicp_result) % 16 == 0, "the fused gather copies records in 16-byte words");
+      alignas(16) dpgicp_result r;
       r.tx = ftx; r.ty = fty;
       r.theta = atan2f(fs, fc);                      /* Rotation2Df::fromRotationMatrix().angle() */
       r.rot_c = fc; r.rot_s = fs;
@@ -1190,7 +1385,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         /* fused gather: seven 16-byte stores per peer, straight into every rank's buffer at the global slot */
         const long long slot = (long long)P.gather_rank + pair * (long long)P.gather_world;
         const int4 *src = reinterpret_cast<const int4 *>(&r);
-        for (int g = 0; g < P.gather_world; ++g) {
+        for (int g = 0; g < P.gather_fanout; ++g) {
           int4 *dst = reinterpret_cast<int4 *>(P.gather_peer[g] + slot);
 #pragma unroll
           for (int q = 0; q < (int)(sizeof(dpgicp_result) / 16); ++q) dst[q] = src[q];
@@ -1353,36 +1548,256 @@ __global__ void ranges_to_rows_kernel(const float *__restrict__ ranges, const in
 }
 
 /* ------------------------------------------------------------------------------------------------
- * Candidate-pair enumeration (reoptimize's distance gate, dpg_slam.cc:79-107): count pass then
- * fill pass; one thread per source node i, output in the reference's (i, j) loop order.
+ * Candidate-pair enumeration on the device (the callers of runIcp: reoptimize dpg_slam.cc:79-107 and
+ * updatePoseGraphObsConstraints dpg_slam.cc:255-300), output left in device memory as the pair batch.
+ *
+ * Pose-graph nodes are created along the trajectory (1 m / 30 deg apart, parameters.h:242,254), so consecutive node
+ * indices are spatially compact — the same property the ICP kernel uses for beam-ordered points.  A hierarchy of
+ * bounding boxes over INDEX ranges (32 nodes per leaf box, 32 boxes per parent, ...) is therefore tight, and
+ * traversing it in index order visits the candidates j of a node i in ascending j: the reference's loop order falls
+ * out without any sort.  One warp per node i walks the hierarchy top-down (32 children tested per step, one per
+ * lane, a ballot per step); the leaf step applies the reference's float gate to 32 nodes at once.  Box lower bounds
+ * use the gate's own rounding sequence, so by monotonicity of rounding the pruning is exact.  A count pass, a device
+ * exclusive scan and a fill pass keep the global order: pair position = start[i] + rank of j among node i's hits.
+ * The fill pass also derives every pair's guess from the node estimates (dpg_slam.cc:364-378).
+ * Worst case (node indices in no spatial order) degrades to all-pairs tests; pose-graph nodes are never like that.
  * ---------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ bool gate_pair(const float2 *xy, const int32_t *pass, int i, int j, float r_same,
-                                          float r_other) {
-  const float dx = __fsub_rn(xy[j].x, xy[i].x), dy = __fsub_rn(xy[j].y, xy[i].y);
+struct NodeBox {               /* 32 bytes: bounding box + pass range of an index range of nodes */
+  float lox, loy, hix, hiy;
+  int32_t pass_lo, pass_hi, pad0, pad1;
+};
+constexpr int kEnumFan = 32;   /* children per box = lanes of the warp testing them */
+constexpr int kEnumMaxLevels = 7;
+
+struct EnumParams {
+  const float2 *xy;            /* node positions                                          */
+  const int32_t *pass;         /* node pass numbers                                       */
+  const float4 *aux;           /* (theta, cosf(-theta), sinf(-theta), 0) per node          */
+  const NodeBox *boxes;        /* level L (1-based) starts at level_off[L - 1]            */
+  long long level_off[kEnumMaxLevels];
+  int32_t level_cnt[kEnumMaxLevels];
+  int32_t levels;
+  int32_t n;
+  float r_same, r_other;
+  unsigned long long *cnt;     /* count pass: pairs per node out; fill pass: start offsets in */
+  PairTask *tasks;             /* fill pass: this shard's pair list                         */
+  int32_t rank, world;
+  unsigned int *amb_count;     /* pairs whose cos/sin sit too close to a binary32 rounding boundary for two */
+  long long *amb_list;         /* libm implementations to be guaranteed to agree: the host re-derives these */
+  int32_t amb_cap;
+};
+
+/* the reference's gate: float distance between two node estimates against the same-pass / other-pass radius */
+__device__ __forceinline__ bool node_gate(float2 a, int pa, float2 b, int pb, float r_same, float r_other) {
+  const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y);
   const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-  return dist <= ((pass[j] == pass[i]) ? r_same : r_other);
+  return dist <= ((pa == pb) ? r_same : r_other);
 }
 
-__global__ void enumerate_count_kernel(const float2 *xy, const int32_t *pass, int n, float r_same, float r_other,
-                                       unsigned long long *cnt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  unsigned long long c = 0;
-  if (i >= 1) {
-    c = 1;
-    for (int j = 0; j < i - 1; ++j) c += gate_pair(xy, pass, i, j, r_same, r_other) ? 1 : 0;
+/* can any node inside `bx` pass the gate against query (q, pq)?  Lower bound of the gate's distance, same roundings */
+__device__ __forceinline__ bool box_may_pass(const NodeBox bx, float2 q, int pq, float r_same, float r_other) {
+  const float ex = fmaxf(fmaxf(__fsub_rn(bx.lox, q.x), __fsub_rn(q.x, bx.hix)), 0.0f);
+  const float ey = fmaxf(fmaxf(__fsub_rn(bx.loy, q.y), __fsub_rn(q.y, bx.hiy)), 0.0f);
+  const float lb = __fsqrt_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+  float r;
+  if (pq < bx.pass_lo || pq > bx.pass_hi) r = r_other;            /* no node of the query's pass inside */
+  else if (bx.pass_lo == bx.pass_hi) r = r_same;                  /* only nodes of the query's pass     */
+  else r = fmaxf(r_same, r_other);
+  return lb <= r;                                                 /* empty boxes have lb = +inf / NaN   */
+}
+
+/* leaf boxes: one warp per box of kEnumFan consecutive nodes */
+__global__ void node_boxes_leaf_kernel(const float2 *__restrict__ xy, const int32_t *__restrict__ pass, int n,
+                                       NodeBox *__restrict__ out, int n_boxes) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= n_boxes) return;
+  const int k = b * kEnumFan + lane;
+  const float inf = __int_as_float(0x7f800000);
+  float lox = inf, loy = inf, hix = -inf, hiy = -inf;
+  int plo = 0x7fffffff, phi = -0x7fffffff - 1;
+  if (k < n) { const float2 p = xy[k]; lox = hix = p.x; loy = hiy = p.y; plo = phi = pass[k]; }
+  lox = warp_min(lox); loy = warp_min(loy); hix = warp_max(hix); hiy = warp_max(hiy);
+  plo = __reduce_min_sync(0xffffffffu, plo); phi = __reduce_max_sync(0xffffffffu, phi);
+  if (lane == 0) { NodeBox o = {lox, loy, hix, hiy, plo, phi, 0, 0}; out[b] = o; }
+}
+
+/* parent boxes: one warp per box of kEnumFan consecutive child boxes */
+__global__ void node_boxes_up_kernel(const NodeBox *__restrict__ in, int n_in, NodeBox *__restrict__ out, int n_out) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= n_out) return;
+  const int k = b * kEnumFan + lane;
+  const float inf = __int_as_float(0x7f800000);
+  float lox = inf, loy = inf, hix = -inf, hiy = -inf;
+  int plo = 0x7fffffff, phi = -0x7fffffff - 1;
+  if (k < n_in) { const NodeBox c = in[k]; lox = c.lox; loy = c.loy; hix = c.hix; hiy = c.hiy; plo = c.pass_lo; phi = c.pass_hi; }
+  lox = warp_min(lox); loy = warp_min(loy); hix = warp_max(hix); hiy = warp_max(hiy);
+  plo = __reduce_min_sync(0xffffffffu, plo); phi = __reduce_max_sync(0xffffffffu, phi);
+  if (lane == 0) { NodeBox o = {lox, loy, hix, hiy, plo, phi, 0, 0}; out[b] = o; }
+}
+
+/* is the double v so close to the midpoint of two adjacent binary32 values that a libm with a different (sub-ulp)
+ * error could round it the other way?  (29 mantissa bits are dropped: the midpoint pattern is 1 followed by zeros) */
+__device__ __forceinline__ bool near_f32_rounding_boundary(double v) {
+  const unsigned low = (unsigned)(__double_as_longlong(v) & 0x1fffffffll);
+  const int d = (int)low - 0x10000000;
+  return (d < 0 ? -d : d) <= 32;
+}
+
+/* the pair task of (source node src, target node tgt): indices + the guess of runIcp (dpg_slam.cc:364-378) in the
+ * arithmetic of dpgicp_relative_guess (math_utils.cc:20-34, math_utils.h:13-16) and of the Matrix4f initialiser */
+__device__ __forceinline__ PairTask make_pair_task(const EnumParams &E, int src, int tgt, long long slot) {
+  const float2 p1 = E.xy[tgt], p2 = E.xy[src];
+  const float4 a1 = E.aux[tgt];
+  const float th2 = E.aux[src].x;
+  const float tx = __fsub_rn(p2.x, p1.x), ty = __fsub_rn(p2.y, p1.y);
+  const float c = a1.y, sn = a1.z;                                   /* Rotation2Df(-theta_1), host libm */
+  PairTask t;
+  t.src = src; t.tgt = tgt;
+  t.tx = __fadd_rn(__fmul_rn(c, tx), __fmul_rn(-sn, ty));
+  t.ty = __fadd_rn(__fmul_rn(sn, tx), __fmul_rn(c, ty));
+  double d = (double)__fsub_rn(th2, a1.x);                           /* AngleMod, evaluated in binary64 */
+  d = __dsub_rn(d, __dmul_rn(6.283185307179586, rint(__ddiv_rn(d, 6.283185307179586))));
+  const double g2 = (double)(float)d;
+  double sd, cd;
+  sincos(g2, &sd, &cd);
+  t.c = (float)cd; t.s = (float)sd;
+  if (near_f32_rounding_boundary(cd) || near_f32_rounding_boundary(sd)) {
+    const unsigned k = atomicAdd(E.amb_count, 1u);
+    if (k < (unsigned)E.amb_cap) E.amb_list[k] = slot;
   }
-  cnt[i] = c;
+  return t;
 }
 
-__global__ void enumerate_fill_kernel(const float2 *xy, const int32_t *pass, int n, float r_same, float r_other,
-                                      const unsigned long long *start, int32_t *src, int32_t *tgt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || i < 1) return;
-  unsigned long long o = start[i];
-  src[o] = i; tgt[o] = i - 1; ++o;
-  for (int j = 0; j < i - 1; ++j)
-    if (gate_pair(xy, pass, i, j, r_same, r_other)) { src[o] = i; tgt[o] = j; ++o; }
+/* DPGICP_ENUM_REOPTIMIZE: one warp per node i.  FILL = false counts node i's pairs into cnt[i]; FILL = true writes
+ * them (E.cnt then holds the exclusive scan of the counts). */
+template <bool FILL>
+__global__ void __launch_bounds__(128) enumerate_reopt_kernel(const EnumParams E) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= E.n) return;
+  unsigned long long count = 0, pos = 0;
+  if (FILL) pos = E.cnt[i];
+  auto emit = [&](unsigned long long at, int src, int tgt) {
+    if ((long long)(at % (unsigned long long)E.world) == (long long)E.rank) {
+      const long long slot = (long long)(at / (unsigned long long)E.world);
+      E.tasks[slot] = make_pair_task(E, src, tgt, slot);
+    }
+  };
+  if (i >= 1) {                                   /* the successive pair comes first (dpg_slam.cc:83-89) */
+    if (FILL && lane == 0) emit(pos, i, i - 1);
+    ++pos; ++count;
+  }
+  const int jmax = i - 1;                          /* gated candidates: j < i - 1 (dpg_slam.cc:91) */
+  if (jmax > 0) {
+    const float2 q = E.xy[i];
+    const int pq = E.pass[i];
+    unsigned mask[kEnumMaxLevels + 1];
+    int base[kEnumMaxLevels + 1];
+    const int top = E.levels;
+    /* span[L] = nodes covered by one box of level L */
+    auto test_boxes = [&](int L, int first) -> unsigned {
+      const int c = first + lane;
+      long long span = kEnumFan;
+      for (int k = 1; k < L; ++k) span *= kEnumFan;
+      bool ok = c < E.level_cnt[L - 1] && (long long)c * span < (long long)jmax;
+      if (ok) ok = box_may_pass(E.boxes[E.level_off[L - 1] + c], q, pq, E.r_same, E.r_other);
+      return __ballot_sync(0xffffffffu, ok);
+    };
+    int level = top;
+    base[top] = 0;
+    mask[top] = test_boxes(top, 0);
+    for (;;) {
+      while (level <= top && mask[level] == 0u) ++level;
+      if (level > top) break;
+      const int b = __ffs(mask[level]) - 1;
+      mask[level] &= mask[level] - 1u;
+      const int idx = base[level] + b;
+      if (level == 1) {
+        const int j = idx * kEnumFan + lane;
+        bool ok = j < jmax;
+        if (ok) ok = node_gate(E.xy[j], E.pass[j], q, pq, E.r_same, E.r_other);
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (FILL && ok) emit(pos + (unsigned long long)__popc(bal & ((1u << lane) - 1u)), i, j);
+        pos += (unsigned long long)__popc(bal);
+        count += (unsigned long long)__popc(bal);
+      } else {
+        --level;
+        base[level] = idx * kEnumFan;
+        mask[level] = test_boxes(level, base[level]);
+      }
+    }
+  }
+  if (!FILL && lane == 0) E.cnt[i] = count;
+}
+
+/* DPGICP_ENUM_ONLINE: the newest node is n-1, the preceding node pre = n-2; candidates i < n-3 are gated against the
+ * PRECEDING node and attach to it.  One warp per chunk of 32 candidates; cnt[chunk] as above.  Pair 0 is the
+ * successive pair (src n-1, tgt n-2), counted with chunk 0. */
+template <bool FILL>
+__global__ void __launch_bounds__(128) enumerate_online_kernel(const EnumParams E, int n_chunks) {
+  const int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (chunk >= n_chunks) return;
+  const int pre = E.n - 2, jmax = E.n - 3;
+  unsigned long long pos = 0;
+  if (FILL) pos = E.cnt[chunk];
+  auto emit = [&](unsigned long long at, int src, int tgt) {
+    if ((long long)(at % (unsigned long long)E.world) == (long long)E.rank) {
+      const long long slot = (long long)(at / (unsigned long long)E.world);
+      E.tasks[slot] = make_pair_task(E, src, tgt, slot);
+    }
+  };
+  unsigned long long count = 0;
+  if (chunk == 0) {
+    if (FILL && lane == 0) emit(pos, E.n - 1, pre);
+    ++pos; ++count;
+  }
+  const int j = chunk * 32 + lane;
+  bool ok = j < jmax;
+  if (ok) ok = node_gate(E.xy[j], E.pass[j], E.xy[pre], E.pass[pre], E.r_same, E.r_other);
+  const unsigned bal = __ballot_sync(0xffffffffu, ok);
+  if (FILL && ok) emit(pos + (unsigned long long)__popc(bal & ((1u << lane) - 1u)), pre, j);
+  count += (unsigned long long)__popc(bal);
+  if (!FILL && lane == 0) E.cnt[chunk] = count;
+}
+
+/* exclusive scan of n 64-bit counts in place, v[n] = total: one CTA (the arrays are a few MB at most and sit in L2) */
+__global__ void __launch_bounds__(1024) scan_u64_kernel(unsigned long long *v, int n) {
+  __shared__ unsigned long long wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + 1023) / 1024;
+  const int lo = tid * per < n ? tid * per : n, hi = lo + per < n ? lo + per : n;
+  unsigned long long sum = 0;
+  for (int k = lo; k < hi; ++k) sum += v[k];
+  unsigned long long incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = wsum[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    wsum[lane] = wi - w;                       /* exclusive prefix of the warp totals */
+    if (lane == 31) v[n] = wi;                 /* grand total */
+  }
+  __syncthreads();
+  unsigned long long run = wsum[warp] + (incl - sum);
+  for (int k = lo; k < hi; ++k) { const unsigned long long t = v[k]; v[k] = run; run += t; }
+}
+
+/* unpack a pair list for the host: indices and the guess entries */
+__global__ void unpack_tasks_kernel(const PairTask *__restrict__ tasks, long long n, int32_t *src, int32_t *tgt, float4 *T) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const PairTask t = tasks[k];
+  if (src) src[k] = t.src;
+  if (tgt) tgt[k] = t.tgt;
+  if (T) T[k] = make_float4(t.c, t.s, t.tx, t.ty);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -292,6 +292,68 @@ class ScanMatcher:
                                                      corr.ctypes.data, d2.ctypes.data))
         return corr[:s.shape[0]], d2[:s.shape[0]]
 
+    def correspondences_seeded(self, source_ds, target_ds, T, params: Params, prev_nn):
+        """The same pass with the sticky tie preference of an ICP run in progress: ``prev_nn[i]`` = forward neighbour
+        of source point i in the previous pass (-1 = none).  Returns (corr_tgt, d2, nn_out)."""
+        s, t = _pts(source_ds), _pts(target_ds)
+        Tm = np.ascontiguousarray(T, np.float32)
+        n = max(s.shape[0], 1)
+        corr = np.full(n, -1, np.int32)
+        d2 = np.zeros(n, np.float32)
+        nn = np.full(n, -1, np.int32)
+        prev = np.ascontiguousarray(prev_nn, np.int32)
+        self._check(self._lib.dpgicp_correspondences_seeded(self._h, s.ctypes.data, s.shape[0], t.ctypes.data, t.shape[0],
+                                                            s.shape[1] * 4, Tm.ctypes.data, C.byref(params),
+                                                            prev.ctypes.data, corr.ctypes.data, d2.ctypes.data, nn.ctypes.data))
+        return corr[:s.shape[0]], d2[:s.shape[0]], nn[:s.shape[0]]
+
+    # ---- device-resident callers: nodes in, pair batch left on the device ------------------------------------
+    def set_nodes(self, node_poses, node_pass):
+        """Pose-graph node estimates (n, 3) = (x, y, theta) and pass numbers; node k owns scan k of the store."""
+        ps = np.ascontiguousarray(node_poses, np.float32).reshape(-1, 3)
+        pa = np.ascontiguousarray(node_pass, np.int32)
+        if ps.shape[0] != pa.shape[0]:
+            raise ValueError("node_poses and node_pass must have the same length")
+        self._check(self._lib.dpgicp_set_nodes(self._h, ps.ctypes.data, pa.ctypes.data, ps.shape[0]))
+
+    def enumerate_pairs_device(self, mode=_abi.ENUM_REOPTIMIZE, same_pass_radius=5.0, other_pass_radius=2.0,
+                               shard_rank=0, shard_world=1) -> Tuple[int, int]:
+        """Build the caller's pair list (``reoptimize`` or ``updatePoseGraphObsConstraints``) and every pair's guess on
+        the device, in the reference's loop order; this context keeps the pairs with global index % world == rank as
+        its batch.  Returns (n_pairs_total, n_pairs_local)."""
+        tot, loc = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.dpgicp_enumerate_pairs_device(self._h, mode, same_pass_radius, other_pass_radius,
+                                                            shard_rank, shard_world, C.byref(tot), C.byref(loc)))
+        self._n_pairs = int(loc.value)
+        return int(tot.value), int(loc.value)
+
+    def fetch_pairs(self, n: Optional[int] = None):
+        """The current batch's pair list: (src_idx, tgt_idx, T (n, 4) = guess entries c, s, tx, ty)."""
+        n = self._n_pairs if n is None else n
+        src = np.zeros(n, np.int32)
+        tgt = np.zeros(n, np.int32)
+        T = np.zeros((n, 4), np.float32)
+        self._check(self._lib.dpgicp_fetch_pairs(self._h, src.ctypes.data, tgt.ctypes.data, T.ctypes.data, n))
+        return src, tgt, T
+
+    def convert_ranges_device(self, device_ptr: int, n_scans: int, n_beams: int, scanner):
+        """Scan store from raw ranges already in device memory (e.g. all-gathered there over NCCL)."""
+        self._check(self._lib.dpgicp_convert_ranges_device(self._h, C.c_void_p(device_ptr), n_scans, n_beams,
+                                                           scanner.angle_min, scanner.angle_max, scanner.range_max,
+                                                           scanner.laser_x, scanner.laser_y, scanner.laser_theta))
+
+    def gather_set_root_only(self, root_only: bool):
+        self._check(self._lib.dpgicp_gather_set_root_only(self._h, int(bool(root_only))))
+
+    def enable_stage_timing(self, on: bool = True):
+        self._check(self._lib.dpgicp_enable_stage_timing(self._h, int(bool(on))))
+
+    def last_run_stage_ms(self):
+        ms = (C.c_float * 8)()
+        n = C.c_int32(0)
+        self._check(self._lib.dpgicp_last_run_stage_ms(self._h, C.byref(ms), C.byref(n)))
+        return [float(ms[k]) for k in range(n.value)]
+
     def enumerate_pairs(self, node_xy, node_pass, same_pass_radius=5.0, other_pass_radius=2.0):
         """Pair list of one ``reoptimize()`` in the reference's loop order (parameters.h:212,224)."""
         xy = np.ascontiguousarray(node_xy, np.float32)

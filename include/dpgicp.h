@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DPGICP_ABI_VERSION 2
+#define DPGICP_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define DPGICP_OK            0
@@ -52,6 +52,12 @@ extern "C" {
                                           * neighbour; one Gauss-Newton step per iteration from the 3x3 normal
                                           * equations (Cholesky); DESIGN.md "point-to-line"               */
 
+/* Tie rule of the exact searches (BRUTE, PRUNED).  FLANN's order among points at EXACTLY the same binary32 distance
+ * is unspecified, so the library fixes one that is cheap on the GPU:
+ *   forward     the neighbour is the point matched in the previous iteration of the same pair when it is among the
+ *               minimisers ("sticky"), else the lowest index among them;
+ *   reciprocal  (i, j) is kept iff no source point is STRICTLY closer to target j than source i (the asker wins ties).
+ * For inputs without exact distance ties this is plain nearest-neighbour search.                                  */
 /* nearest-neighbour search strategy; BRUTE and PRUNED are exact and give identical correspondences */
 #define DPGICP_SEARCH_BRUTE   0
 #define DPGICP_SEARCH_PRUNED  1          /* beam-order block bounding boxes + seeded bound       */
@@ -67,6 +73,20 @@ extern "C" {
                                           * matched target point taken back to the source frame by the inverse of the current
                                           * transform, searched keys = the untransformed source scan, distances to the current
                                           * source points.  Defined by oracle/dpg_oracle.c (orc_correspondences_ex).      */
+
+/* outlier rejection after the reciprocal test (north-star "outlier-trim logic").  The reference registers no
+ * correspondence rejector (dpg_slam.cc:408-412; setRANSACIterations is inert in stock PCL ICP), so the default is
+ * NONE; the other modes are defined by oracle/dpg_oracle.c (orc_outlier_threshold).  K = accepted correspondences of
+ * the pass, d2 their squared distances (binary32):
+ *   TRIMMED  keep_n = max(3, floor(outlier_param * K)); tau = keep_n-th smallest d2; keep d2 <= tau
+ *            (PCL CorrespondenceRejectorTrimmed with overlap ratio outlier_param in (0, 1]);
+ *   MEDIAN   med = d2 of rank K / 2; tau = largest binary32 <= (double)med * outlier_param; keep d2 <= tau
+ *            (PCL CorrespondenceRejectorMedianDistance with factor outlier_param > 0).
+ * Ties at tau are all kept, so the kept set does not depend on any ordering of equal values.  The same rejector is
+ * applied to the correspondences the CENSI_CORR covariance is formed on.                                          */
+#define DPGICP_OUTLIER_NONE    0
+#define DPGICP_OUTLIER_TRIMMED 1
+#define DPGICP_OUTLIER_MEDIAN  2
 
 /* what is written to result.cov (SURVEY.md §8a "covariance modes") */
 #define DPGICP_COV_REFERENCE_LIVE  0     /* diag(sx2, sy2, st2): cov_func_point_to_point.h:572-575 */
@@ -106,6 +126,9 @@ typedef struct dpgicp_params {
   int32_t projective_window;           /* 8      DPGICP_SEARCH_PROJECTIVE only: W, candidates on each side (1..1024)   */
   float   sensor_x, sensor_y;          /* 0.2, 0 DPGICP_SEARCH_PROJECTIVE only: laser origin in the cloud (base_link)
                                         *        frame, parameters.h:319-339 — the centre the beam order turns around  */
+  int32_t outlier_mode;                /* DPGICP_OUTLIER_* (default NONE = stock PCL ICP, dpg_slam.cc:408-412)        */
+  int32_t reserved0;                   /* 0                                                                           */
+  double  outlier_param;               /* TRIMMED: overlap ratio in (0, 1]; MEDIAN: factor > 0                         */
 } dpgicp_params;
 
 /* ---- fixed-size result record (112 bytes) ------------------------------------------------- */
@@ -257,6 +280,15 @@ int  dpgicp_correspondences(dpgicp_ctx *ctx,
                             const float T[4] /* c, s, tx, ty */, const dpgicp_params *params,
                             int32_t *corr_tgt, float *corr_d2);
 
+/* The same pass with the tie preference of an ICP run in progress: prev_nn[i] = forward neighbour of source point i
+ * in the previous pass (-1 = none; NULL = all none, i.e. dpgicp_correspondences), nn_out[i] (may be NULL) = this
+ * pass's gated forward neighbour — what the next pass would be seeded with.                                      */
+int  dpgicp_correspondences_seeded(dpgicp_ctx *ctx,
+                                   const void *source_points, int32_t n_source,
+                                   const void *target_points, int32_t n_target, size_t stride_bytes,
+                                   const float T[4], const dpgicp_params *params, const int32_t *prev_nn,
+                                   int32_t *corr_tgt, float *corr_d2, int32_t *nn_out);
+
 /* ---- candidate-pair enumeration (callers' distance gate, dpg_slam.cc:91-98,275-282) ---------- */
 /* For node i (ascending) and every j < i-1 ... emits (src=i, tgt=j) when the node positions are
  * within same_pass_radius (same pass) or other_pass_radius (different pass), plus every
@@ -265,6 +297,50 @@ int  dpgicp_correspondences(dpgicp_ctx *ctx,
 int  dpgicp_enumerate_pairs(dpgicp_ctx *ctx, const float *node_xy, const int32_t *node_pass,
                             int32_t n_nodes, float same_pass_radius, float other_pass_radius,
                             int32_t *src_idx, int32_t *tgt_idx, int64_t *n_pairs);
+
+/* ---- device-resident form of the callers (pose-graph nodes in, pair batch left on the device) --------------
+ * Node k of the pose graph owns scan k of the store.  dpgicp_set_nodes uploads the node estimates
+ * (x, y, theta per node, DpgNode::getEstimatedPosition) and pass numbers.  dpgicp_enumerate_pairs_device then builds
+ * the pair list of one caller ON THE DEVICE, in the reference's loop order, together with every pair's guess
+ * (dpg_slam.cc:364-378, the arithmetic of dpgicp_relative_guess + the Matrix4f cos/sin), and leaves it as the
+ * context's current batch: dpgicp_run / fetch_results / fetch_factors follow with no host round trip of the list.
+ *   DPGICP_ENUM_REOPTIMIZE  DpgSLAM::reoptimize (dpg_slam.cc:79-107): for i = 1..n-1: (src i, tgt i-1), then every
+ *                           j < i-1 within same_pass_radius / other_pass_radius of node i -> (src i, tgt j).
+ *   DPGICP_ENUM_ONLINE      DpgSLAM::updatePoseGraphObsConstraints (dpg_slam.cc:255-300) for new node n-1 with
+ *                           preceding node n-2: (src n-1, tgt n-2), then every i <= n-4 within the radius of the
+ *                           PRECEDING node -> (src n-2, tgt i)   [loop closures attach to the preceding node and the
+ *                           loop runs to dpg_nodes_.size() - 2 exclusive, dpg_slam.cc:275-299].
+ * Sharding: of the global list only the pairs with (global index % shard_world) == shard_rank become this context's
+ * batch (round-robin, as the multi-GPU path shards); local pair k is global pair shard_rank + k * shard_world.
+ * n_pairs_total / n_pairs_local (may be NULL) receive the global and the local count.                          */
+#define DPGICP_ENUM_REOPTIMIZE 0
+#define DPGICP_ENUM_ONLINE     1
+int  dpgicp_set_nodes(dpgicp_ctx *ctx, const float *node_pose_xytheta, const int32_t *node_pass, int32_t n_nodes);
+int  dpgicp_enumerate_pairs_device(dpgicp_ctx *ctx, int32_t mode, float same_pass_radius, float other_pass_radius,
+                                   int32_t shard_rank, int32_t shard_world, int64_t *n_pairs_total,
+                                   int64_t *n_pairs_local);
+/* the current batch's pair list back on the host (any of the outputs may be NULL): indices and the guess as the
+ * Matrix4f entries T = (T(0,0), T(1,0), T(0,3), T(1,3)) per pair                                                */
+int  dpgicp_fetch_pairs(dpgicp_ctx *ctx, int32_t *src_idx, int32_t *tgt_idx, float *T, int64_t n_pairs);
+/* scan store from raw ranges that are ALREADY in device memory (e.g. all-gathered there over NCCL); same conversion
+ * as dpgicp_upload_ranges                                                                                       */
+int  dpgicp_convert_ranges_device(dpgicp_ctx *ctx, const float *d_ranges, int32_t n_scans, int32_t n_beams,
+                                  float angle_min, float angle_max, float range_max,
+                                  float laser_x, float laser_y, float laser_theta);
+
+/* ---- single-process multi-GPU (host code in C/C++: one context per GPU driven by one thread) ----------------
+ * The fused gather for contexts that live in ONE process: instead of CUDA IPC handles the contexts are given each
+ * other's gather buffers directly (peer access is enabled between their devices).  ctxs[r] becomes rank r of
+ * `world`; every context allocates a buffer for n_global_pairs records.  root_only != 0: records are stored only
+ * into rank 0's buffer (what a single host-side pose-graph update needs) instead of into every rank's.          */
+int  dpgicp_gather_attach_local(dpgicp_ctx **ctxs, int32_t world, int64_t n_global_pairs, int32_t root_only);
+/* the cross-process form (dpgicp_gather_export / _attach) with root_only != 0 stores into rank 0's buffer only; set
+ * before dpgicp_run, on every rank alike                                                                        */
+int  dpgicp_gather_set_root_only(dpgicp_ctx *ctx, int32_t root_only);
+/* device time of every stage launch of dpgicp_run (CUDA events between the launches of the stage chain): switch it
+ * on, run, then read the last run's per-stage times in ms (synchronises on the last stage); *n_stages <= 8       */
+int  dpgicp_enable_stage_timing(dpgicp_ctx *ctx, int32_t on);
+int  dpgicp_last_run_stage_ms(dpgicp_ctx *ctx, float stage_ms[8], int32_t *n_stages);
 
 /* ---- measurement aid ------------------------------------------------------------------------- */
 /* Measures this device's FP32 CUDA-core throughput with the two instruction mixes that matter for

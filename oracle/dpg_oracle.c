@@ -12,7 +12,11 @@
  *                     (Matrix4f * Vector4f evaluated column by column, PCL transformCloud)
  *   distance          d2 = (dx*dx) + (dy*dy), dx = px - qx, dy = py - qy           binary32, no FMA
  *                     (FLANN L2_Simple accumulates diff*diff in coordinate order; z term is +0)
- *   nearest neighbour argmin over (d2, index) lexicographically  (lowest index wins ties)
+ *   nearest neighbour minimum d2; among exact ties the point matched in the previous pass of the same pair wins
+ *                     ("sticky"), else the lowest index.  FLANN's tie order is unspecified;
+ *                     this rule lets the GPU skip the index bookkeeping whenever nothing strictly improves.
+ *   reciprocity       pair (i, j) is kept iff no source point is STRICTLY closer to target j than i is
+ *                     (the asker wins exact ties)
  *   gate              d2 <= fl32_floor(max_correspondence_distance^2 computed in binary64)
  *   moment sums       exact int64 fixed point: round-to-nearest-even of value * 2^S
  *                     S = 32 for sums of coordinates, 28 for sums of coordinate products,
@@ -294,21 +298,73 @@ static int correspondences_projective(const float *src_t, int ns, const float *t
   return K;
 }
 
+/* ---- outlier rejection (north-star "outlier-trim logic"; the reference registers no rejector — dpg_slam.cc:408-412 —
+ * so this is OFF by default and defined HERE).  Both modes need one order statistic of the accepted squared
+ * distances (binary32, compared as numbers; ties at the threshold are all kept, so the result does not depend on
+ * any ordering of equal values):
+ *   DPGICP_OUTLIER_TRIMMED  (PCL CorrespondenceRejectorTrimmed analogue): keep_n = max(3, floor(param * K));
+ *                           tau = keep_n-th smallest d2; keep d2 <= tau.
+ *   DPGICP_OUTLIER_MEDIAN   (PCL CorrespondenceRejectorMedianDistance analogue): med = sorted d2 [K / 2];
+ *                           tau = largest binary32 <= (double)med * param; keep d2 <= tau.                    */
+static int cmp_f32(const void *a, const void *b) {
+  const float x = *(const float *)a, y = *(const float *)b;
+  return (x > y) - (x < y);
+}
+
+float orc_outlier_threshold(const float *d2_accepted, int K, const dpgicp_params *p) {
+  if (p->outlier_mode == DPGICP_OUTLIER_NONE || K < 1) return INFINITY;
+  float *v = (float *)malloc(sizeof(float) * (size_t)K);
+  memcpy(v, d2_accepted, sizeof(float) * (size_t)K);
+  qsort(v, (size_t)K, sizeof(float), cmp_f32);
+  float tau;
+  if (p->outlier_mode == DPGICP_OUTLIER_TRIMMED) {
+    int keep = (int)floor(p->outlier_param * (double)K);
+    if (keep < 3) keep = 3;
+    if (keep > K) keep = K;
+    tau = v[keep - 1];
+  } else {
+    const double lim = (double)v[K / 2] * p->outlier_param;
+    tau = (float)lim;
+    if ((double)tau > lim) tau = nextafterf(tau, -INFINITY);
+  }
+  free(v);
+  return tau;
+}
+
+static int reject_outliers(int ns, const dpgicp_params *p, int32_t *corr, const float *d2, int K) {
+  if (p->outlier_mode == DPGICP_OUTLIER_NONE || K < 1) return K;
+  float *acc = (float *)malloc(sizeof(float) * (size_t)K);
+  int k = 0;
+  for (int i = 0; i < ns; ++i) if (corr[i] >= 0) acc[k++] = d2[i];
+  const float tau = orc_outlier_threshold(acc, K, p);
+  free(acc);
+  int kept = 0;
+  for (int i = 0; i < ns; ++i) {
+    if (corr[i] < 0) continue;
+    if (d2[i] <= tau) ++kept; else corr[i] = -1;
+  }
+  return kept;
+}
+
 /* PCL CorrespondenceEstimation::determine[Reciprocal]Correspondences (Appendix A.3-2): for each
  * source index in order: forward NN, gate, reciprocal NN over the *current* source, require i' == i.
  * src_orig / T (the untransformed source and the transform that produced src_t) are only read by
- * DPGICP_SEARCH_PROJECTIVE; NULL means "src_t is the original, T = identity". */
-int orc_correspondences_ex(const float *src_t, int ns, const float *tgt, int nt, const dpgicp_params *p, int fast,
-                           const float *src_orig, const float *T, int32_t *corr, float *d2) {
+ * DPGICP_SEARCH_PROJECTIVE; NULL means "src_t is the original, T = identity".
+ * prev_nn (size ns, may be NULL; exact searches only) carries the forward neighbour of the previous pass of the same
+ * pair: in: the tie preference (-1 = none), out: this pass's gated forward neighbour (-1 = none within the gate).
+ * d2 is a required scratch/output array of ns floats.                                                          */
+int orc_correspondences_seeded(const float *src_t, int ns, const float *tgt, int nt, const dpgicp_params *p, int fast,
+                               const float *src_orig, const float *T, int32_t *prev_nn, int32_t *corr, float *d2) {
   const float thr = gate_threshold(p);
   int K = 0;
   if (ns <= 0 || nt <= 0) {
-    for (int i = 0; i < ns; ++i) { corr[i] = -1; if (d2) d2[i] = INFINITY; }
+    for (int i = 0; i < ns; ++i) { corr[i] = -1; d2[i] = INFINITY; if (prev_nn) prev_nn[i] = -1; }
     return 0;
   }
   if (p->search == DPGICP_SEARCH_PROJECTIVE) {
     static const float ident[4] = {1.0f, 0.0f, 0.0f, 0.0f};
-    return correspondences_projective(src_t, ns, tgt, nt, p, src_orig ? src_orig : src_t, T ? T : ident, corr, d2);
+    K = correspondences_projective(src_t, ns, tgt, nt, p, src_orig ? src_orig : src_t, T ? T : ident, corr, d2);
+    return reject_outliers(ns, p, corr, d2, K);
   }
   grid_t gt, gs;
   if (fast) {
@@ -322,12 +378,18 @@ int orc_correspondences_ex(const float *src_t, int ns, const float *tgt, int nt,
     corr[i] = -1;
     if (fast) nn_grid(&gt, src_t[2 * i], src_t[2 * i + 1], tgt, &j, &d);
     else nn_brute(src_t[2 * i], src_t[2 * i + 1], tgt, nt, &j, &d);
-    if (d2) d2[i] = d;
+    d2[i] = d;
+    const int seed = prev_nn ? prev_nn[i] : -1;
+    if (prev_nn) prev_nn[i] = -1;
     if (j < 0 || d > thr) continue;
+    /* sticky tie rule: last pass's neighbour wins when it is among the minimisers */
+    if (seed >= 0 && seed < nt && seed != j && dist2(src_t[2 * i], src_t[2 * i + 1], tgt[2 * seed], tgt[2 * seed + 1]) == d) j = seed;
+    if (prev_nn) prev_nn[i] = j;
     if (p->use_reciprocal) {
       if (fast) nn_grid(&gs, tgt[2 * j], tgt[2 * j + 1], src_t, &ir, &dr);
       else nn_brute(tgt[2 * j], tgt[2 * j + 1], src_t, ns, &ir, &dr);
-      if (dr > thr || ir != i) continue;
+      (void)ir;
+      if (dr < d) continue;          /* some source point is strictly closer to target j: not reciprocal */
     }
     corr[i] = j;
     ++K;
@@ -336,6 +398,15 @@ int orc_correspondences_ex(const float *src_t, int ns, const float *tgt, int nt,
     grid_free(&gt);
     if (p->use_reciprocal) grid_free(&gs);
   }
+  return reject_outliers(ns, p, corr, d2, K);
+}
+
+int orc_correspondences_ex(const float *src_t, int ns, const float *tgt, int nt, const dpgicp_params *p, int fast,
+                           const float *src_orig, const float *T, int32_t *corr, float *d2) {
+  float *tmp = NULL;
+  if (!d2) d2 = tmp = (float *)malloc(sizeof(float) * (size_t)(ns > 0 ? ns : 1));
+  const int K = orc_correspondences_seeded(src_t, ns, tgt, nt, p, fast, src_orig, T, NULL, corr, d2);
+  free(tmp);
   return K;
 }
 
@@ -509,8 +580,8 @@ static void compose(const float st[4], float fin[4]) {
   fin[0] = nc; fin[1] = ns; fin[2] = ntx; fin[3] = nty;
 }
 
-void orc_icp(const float *src, int ns, const float *tgt, int nt, const float guess[3],
-             const dpgicp_params *p, int fast, dpgicp_result *out, orc_trace *trace) {
+void orc_icp_ex(const float *src, int ns, const float *tgt, int nt, const float guess[3],
+                const dpgicp_params *p, int fast, dpgicp_result *out, orc_trace *trace, int32_t *nn_state) {
   float fin[4];
   orc_guess_matrix(guess, fin);
   out->iterations = 0;
@@ -522,6 +593,11 @@ void orc_icp(const float *src, int ns, const float *tgt, int nt, const float gue
   float *cur = (float *)malloc(sizeof(float) * 2 * (size_t)(ns > 0 ? ns : 1));
   int32_t *corr = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ns > 0 ? ns : 1));
   float *d2 = (float *)malloc(sizeof(float) * (size_t)(ns > 0 ? ns : 1));
+  /* forward neighbour of the previous pass (the sticky tie preference); the caller's copy ends up holding the last
+   * pass's, which seeds the covariance pass at the final pose exactly as the CUDA path's shared-memory array does */
+  int32_t *nn_own = NULL;
+  if (!nn_state) nn_state = nn_own = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ns > 0 ? ns : 1));
+  for (int i = 0; i < ns; ++i) nn_state[i] = -1;
   /* A.2: the guess is applied to the source once, then steps are applied incrementally */
   orc_transform_points(fin, src, ns, cur);
 
@@ -533,7 +609,7 @@ void orc_icp(const float *src, int ns, const float *tgt, int nt, const float gue
     if (trace && trace->count < trace->capacity) {
       memcpy(trace->T_iter + 4 * trace->count, fin, sizeof(fin));
     }
-    int K = orc_correspondences_ex(cur, ns, tgt, nt, p, fast, src, fin, corr, d2);
+    int K = orc_correspondences_seeded(cur, ns, tgt, nt, p, fast, src, fin, nn_state, corr, d2);
     if (trace && trace->count < trace->capacity) trace->n_corr[trace->count++] = K;
     out->n_correspondences = K;
     if (K < 3) {                                   /* A.3-4: min_number_correspondences_ = 3 */
@@ -585,7 +661,12 @@ void orc_icp(const float *src, int ns, const float *tgt, int nt, const float gue
   out->ty = fin[3];
   out->theta = atan2f(fin[1], fin[0]);             /* Rotation2Df::fromRotationMatrix().angle() */
   out->status = status;
-  free(cur); free(corr); free(d2);
+  free(cur); free(corr); free(d2); free(nn_own);
+}
+
+void orc_icp(const float *src, int ns, const float *tgt, int nt, const float guess[3],
+             const dpgicp_params *p, int fast, dpgicp_result *out, orc_trace *trace) {
+  orc_icp_ex(src, ns, tgt, nt, guess, p, fast, out, trace, NULL);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -680,7 +761,8 @@ void orc_run_pair(const float *source_full, int n_source, const float *target_fu
   float *tgt = (float *)malloc(sizeof(float) * 2 * (size_t)(n_target > 0 ? n_target : 1));
   const int ns = orc_downsample(source_full, n_source, div, src);     /* dpg_slam.cc:397-402 */
   const int nt = orc_downsample(target_full, n_target, div, tgt);
-  orc_icp(src, ns, tgt, nt, guess, p, fast, out, NULL);               /* dpg_slam.cc:404-416 */
+  int32_t *nn_state = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ns > 0 ? ns : 1));
+  orc_icp_ex(src, ns, tgt, nt, guess, p, fast, out, NULL, nn_state);  /* dpg_slam.cc:404-416 */
 
   const float live[3] = {p->laser_x_variance, p->laser_y_variance, p->laser_theta_variance};
   const float T[4] = {out->rot_c, out->rot_s, out->tx, out->ty};
@@ -701,8 +783,10 @@ void orc_run_pair(const float *source_full, int n_source, const float *target_fu
     int32_t *corr = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ns > 0 ? ns : 1));
     float *P = (float *)malloc(sizeof(float) * 2 * (size_t)(ns > 0 ? ns : 1));
     float *Q = (float *)malloc(sizeof(float) * 2 * (size_t)(ns > 0 ? ns : 1));
+    float *cd2 = (float *)malloc(sizeof(float) * (size_t)(ns > 0 ? ns : 1));
     orc_transform_points(T, src, ns, cur);
-    orc_correspondences_ex(cur, ns, tgt, nt, p, fast, src, T, corr, NULL);
+    orc_correspondences_seeded(cur, ns, tgt, nt, p, fast, src, T, nn_state, corr, cd2);
+    free(cd2);
     int k = 0;
     for (int i = 0; i < ns; ++i)
       if (corr[i] >= 0) {
@@ -715,7 +799,7 @@ void orc_run_pair(const float *source_full, int n_source, const float *target_fu
     out->status |= orc_cov_censi(P, Q, k, nd, T, p->cov_sensor_variance, live, out->cov, NULL);
     free(cur); free(corr); free(P); free(Q);
   }
-  free(src); free(tgt);
+  free(src); free(tgt); free(nn_state);
 }
 
 int orc_run_batch(const float *points, const int64_t *offsets, int n_scans,
@@ -793,6 +877,33 @@ int64_t orc_enumerate_pairs(const float *node_xy, const int32_t *node_pass, int 
       float thr = (node_pass[j] == node_pass[i]) ? same_pass_radius : other_pass_radius;
       if (dist <= thr) {
         if (n < capacity) { src_idx[n] = i; tgt_idx[n] = j; }
+        ++n;
+      }
+    }
+  }
+  return n;
+}
+
+/* dpg_slam.cc:255-300 (updatePoseGraphObsConstraints): dpg_nodes_ holds nodes 0 .. n-2 (preceding = n-2), the new
+ * node is n-1.  Loop closures compare against and attach to the PRECEDING node (dpg_slam.cc:278,295,299); the loop
+ * runs over i < dpg_nodes_.size() - 2 (dpg_slam.cc:275). */
+int64_t orc_enumerate_online(const float *node_xy, const int32_t *node_pass, int n_nodes,
+                             float same_pass_radius, float other_pass_radius,
+                             int32_t *src_idx, int32_t *tgt_idx, int64_t capacity) {
+  int64_t n = 0;
+  if (n_nodes < 2) return 0;
+  const int nw = n_nodes - 1, pre = n_nodes - 2;
+  if (n < capacity) { src_idx[n] = nw; tgt_idx[n] = pre; }
+  ++n;
+  const int size = n_nodes - 1;                       /* dpg_nodes_.size() before the push */
+  if (size > 1) {
+    for (int i = 0; i < size - 2; ++i) {
+      float dx = node_xy[2 * i] - node_xy[2 * pre];
+      float dy = node_xy[2 * i + 1] - node_xy[2 * pre + 1];
+      float dist = sqrtf((dx * dx) + (dy * dy));
+      float thr = (node_pass[i] == node_pass[pre]) ? same_pass_radius : other_pass_radius;
+      if (dist <= thr) {
+        if (n < capacity) { src_idx[n] = pre; tgt_idx[n] = i; }
         ++n;
       }
     }

@@ -57,6 +57,13 @@ int   orc_correspondences(const float *src_t, int ns, const float *tgt, int nt,
  * and T = (c, s, tx, ty), the transform that produced src_t; both NULL = src_t is the original, T = identity */
 int   orc_correspondences_ex(const float *src_t, int ns, const float *tgt, int nt, const dpgicp_params *p, int fast,
                              const float *src_orig, const float *T, int32_t *corr, float *d2);
+/* the general form: prev_nn (size ns, may be NULL) is the sticky tie preference in / this pass's gated forward neighbour
+ * out (exact searches; see the tie rule in include/dpgicp.h); d2 must be an array of ns floats; the outlier rejector
+ * of p->outlier_mode is applied last                                                                             */
+int   orc_correspondences_seeded(const float *src_t, int ns, const float *tgt, int nt, const dpgicp_params *p, int fast,
+                                 const float *src_orig, const float *T, int32_t *prev_nn, int32_t *corr, float *d2);
+/* rejection threshold tau of DPGICP_OUTLIER_* for K accepted squared distances (+inf for NONE) */
+float orc_outlier_threshold(const float *d2_accepted, int K, const dpgicp_params *p);
 /* bearing key of DPGICP_SEARCH_PROJECTIVE (include/dpgicp.h) */
 float orc_beam_key(float px, float py, float ox, float oy);
 
@@ -74,6 +81,9 @@ typedef struct orc_trace {
  * correspondences of the last executed iteration.                                              */
 void  orc_icp(const float *src, int ns, const float *tgt, int nt, const float guess[3],
               const dpgicp_params *p, int fast, dpgicp_result *out, orc_trace *trace);
+/* the same; nn_state (size ns, may be NULL) receives the last pass's forward neighbours (seeds of the covariance pass) */
+void  orc_icp_ex(const float *src, int ns, const float *tgt, int nt, const float guess[3],
+                 const dpgicp_params *p, int fast, dpgicp_result *out, orc_trace *trace, int32_t *nn_state);
 
 /* ---- a6: covariance ---------------------------------------------------------------------------- */
 /* Censi/Prakhya planar form on index-paired arrays P[k] <-> Q[k]:
@@ -101,6 +111,13 @@ void  orc_factor(const dpgicp_result *rec, int32_t src, int32_t tgt, dpgicp_fact
 int64_t orc_enumerate_pairs(const float *node_xy, const int32_t *node_pass, int n_nodes,
                             float same_pass_radius, float other_pass_radius,
                             int32_t *src_idx, int32_t *tgt_idx, int64_t capacity);
+
+/* updatePoseGraphObsConstraints (dpg_slam.cc:255-300) for the newest node n-1 with preceding node n-2: the successive
+ * pair (src n-1, tgt n-2), then every i < n-3 (the loop bound dpg_nodes_.size() - 2 with size = n-1) within the gate of
+ * the PRECEDING node -> (src n-2, tgt i)                                                                           */
+int64_t orc_enumerate_online(const float *node_xy, const int32_t *node_pass, int n_nodes,
+                             float same_pass_radius, float other_pass_radius,
+                             int32_t *src_idx, int32_t *tgt_idx, int64_t capacity);
 
 #ifdef __cplusplus
 }

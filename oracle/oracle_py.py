@@ -49,6 +49,12 @@ def lib() -> C.CDLL:
         L.orc_correspondences.argtypes = [vp, C.c_int, vp, C.c_int, PP, C.c_int, vp, vp]
         L.orc_correspondences_ex.restype = C.c_int
         L.orc_correspondences_ex.argtypes = [vp, C.c_int, vp, C.c_int, PP, C.c_int, vp, vp, vp, vp]
+        L.orc_correspondences_seeded.restype = C.c_int
+        L.orc_correspondences_seeded.argtypes = [vp, C.c_int, vp, C.c_int, PP, C.c_int, vp, vp, vp, vp, vp]
+        L.orc_outlier_threshold.restype = f
+        L.orc_outlier_threshold.argtypes = [vp, C.c_int, PP]
+        L.orc_enumerate_online.restype = i64
+        L.orc_enumerate_online.argtypes = [vp, vp, C.c_int, f, f, vp, vp, i64]
         L.orc_beam_key.restype = f
         L.orc_beam_key.argtypes = [f, f, f, f]
         L.orc_icp.restype = None
@@ -125,18 +131,30 @@ def transform_points(T, xy) -> np.ndarray:
     return out
 
 
-def correspondences(src_t, tgt, params: Params, fast=0, src_orig=None, T=None):
+def correspondences(src_t, tgt, params: Params, fast=0, src_orig=None, T=None, prev_nn=None):
     """One correspondence pass.  ``src_orig`` / ``T`` (the untransformed source and the (c, s, tx, ty)
-    that produced ``src_t``) are only read by SEARCH_PROJECTIVE."""
+    that produced ``src_t``) are only read by SEARCH_PROJECTIVE.  ``prev_nn`` (int32 per source point, -1 = none) is the
+    sticky tie preference of an ICP run in progress; when given, a 4th value is returned: this pass's gated forward
+    neighbours (the next pass's ``prev_nn``)."""
     s, t = _f32(src_t), _f32(tgt)
     corr = np.full(s.shape[0], -1, np.int32)
-    d2 = np.zeros(s.shape[0], np.float32)
+    d2 = np.zeros(max(s.shape[0], 1), np.float32)
     so = _f32(src_orig) if src_orig is not None else None
     tt = _f32(T) if T is not None else None
-    k = lib().orc_correspondences_ex(s.ctypes.data, s.shape[0], t.ctypes.data, t.shape[0],
-                                     C.byref(params), fast, so.ctypes.data if so is not None else None,
-                                     tt.ctypes.data if tt is not None else None, corr.ctypes.data, d2.ctypes.data)
+    nn = np.ascontiguousarray(prev_nn, np.int32).copy() if prev_nn is not None else None
+    k = lib().orc_correspondences_seeded(s.ctypes.data, s.shape[0], t.ctypes.data, t.shape[0],
+                                         C.byref(params), fast, so.ctypes.data if so is not None else None,
+                                         tt.ctypes.data if tt is not None else None,
+                                         nn.ctypes.data if nn is not None else None, corr.ctypes.data, d2.ctypes.data)
+    d2 = d2[:s.shape[0]]
+    if nn is not None:
+        return k, corr, d2, nn
     return k, corr, d2
+
+
+def outlier_threshold(d2_accepted, params: Params) -> float:
+    d = _f32(d2_accepted)
+    return float(lib().orc_outlier_threshold(d.ctypes.data, d.shape[0], C.byref(params)))
 
 
 def icp(src, tgt, guess, params: Params, fast=0, trace=False):
@@ -195,6 +213,18 @@ def enumerate_pairs(node_xy, node_pass, same_radius, other_radius):
     tgt = np.zeros(n, np.int32)
     lib().orc_enumerate_pairs(xy.ctypes.data, ps.ctypes.data, xy.shape[0], same_radius, other_radius,
                               src.ctypes.data, tgt.ctypes.data, n)
+    return src, tgt
+
+
+def enumerate_online(node_xy, node_pass, same_radius, other_radius):
+    """Pair list of one updatePoseGraphObsConstraints call for the newest node (dpg_slam.cc:255-300)."""
+    xy = _f32(node_xy)
+    ps = np.ascontiguousarray(node_pass, np.int32)
+    n = lib().orc_enumerate_online(xy.ctypes.data, ps.ctypes.data, xy.shape[0], same_radius, other_radius, None, None, 0)
+    src = np.zeros(n, np.int32)
+    tgt = np.zeros(n, np.int32)
+    lib().orc_enumerate_online(xy.ctypes.data, ps.ctypes.data, xy.shape[0], same_radius, other_radius,
+                               src.ctypes.data, tgt.ctypes.data, n)
     return src, tgt
 
 

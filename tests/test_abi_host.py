@@ -33,10 +33,24 @@ def test_header_symbols_all_exported_and_bound():
     assert set(declared) <= exported
 
 
-def test_struct_layouts_match_header():
-    assert C.sizeof(Params) == 80 and C.sizeof(Result) == 112
+def test_struct_layouts_match_header(tmp_path):
+    assert C.sizeof(Params) == 96 and C.sizeof(Result) == 112
     assert Result.cov.offset == 40 and Result.mse.offset == 32 and Result.status.offset == 24
     assert _abi.RESULT_DTYPE.fields["cov"][1] == 40 and _abi.RESULT_DTYPE.itemsize == 112
+    # the header itself, compiled as C: sizes and the offset of every params field against the ctypes mirror
+    fields = [f[0] for f in Params._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dpgicp.h"\nint main(void) {\n'
+                   '  printf("%zu %zu %zu %d\\n", sizeof(dpgicp_params), sizeof(dpgicp_result), sizeof(dpgicp_factor), DPGICP_ABI_VERSION);\n'
+                   + "".join(f'  printf("{f} %zu\\n", offsetof(dpgicp_params, {f}));\n' for f in fields)
+                   + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert out[0].split() == [str(C.sizeof(Params)), "112", str(_abi.FACTOR_DTYPE.itemsize), str(_abi.ABI_VERSION)]
+    for line, f in zip(out[1:], fields):
+        name, off = line.split()
+        assert name == f and int(off) == getattr(Params, f).offset, f
 
 
 def test_default_params_are_the_reference_values():
@@ -48,6 +62,7 @@ def test_default_params_are_the_reference_values():
     assert (p.transformation_epsilon, p.max_correspondence_distance, p.cov_sensor_variance) == (5e-9, 0.6, 0.01)
     assert (p.laser_x_variance, p.laser_y_variance) == (0.5, 0.5) and p.laser_theta_variance == np.float32(0.3)
     assert p.cov_cap == 200 and p.cov_mode == _abi.COV_REFERENCE_LIVE and p.metric == _abi.METRIC_POINT_TO_POINT
+    assert p.outlier_mode == _abi.OUTLIER_NONE and p.outlier_param == 0.0      # dpg_slam.cc:408-412 registers no rejector
     assert bytes(p) == bytes(Params.defaults())
     assert lib.dpgicp_default_params(None) == -1
 
