@@ -116,7 +116,8 @@ EXPORTS = [
     "dpgicp_enumerate_pairs", "dpgicp_relative_guess", "dpgicp_fp32_probe", "dpgicp_fp32x2_probe",
     "dpgicp_correspondences_seeded", "dpgicp_set_nodes", "dpgicp_enumerate_pairs_device", "dpgicp_fetch_pairs",
     "dpgicp_convert_ranges_device", "dpgicp_gather_attach_local", "dpgicp_gather_set_root_only",
-    "dpgicp_enable_stage_timing", "dpgicp_last_run_stage_ms",
+    "dpgicp_enable_stage_timing", "dpgicp_last_run_stage_ms", "dpgicp_run_range", "dpgicp_fetch_results_range",
+    "dpgicp_gather_fetch_range", "dpgicp_gather_declare",
 ]
 
 _lib = None
@@ -162,6 +163,7 @@ def load_library() -> C.CDLL:
         "dpgicp_results_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "dpgicp_gather_export": (C.c_int, [vp, i64, vp]),
         "dpgicp_gather_attach": (C.c_int, [vp, vp, i32, i32]),
+        "dpgicp_gather_declare": (C.c_int, [vp, i64, vp]),
         "dpgicp_gather_detach": (C.c_int, [vp]),
         "dpgicp_gather_fetch": (C.c_int, [vp, vp, i64]),
         "dpgicp_gather_device_ptr": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
@@ -184,6 +186,9 @@ def load_library() -> C.CDLL:
         "dpgicp_gather_set_root_only": (C.c_int, [vp, i32]),
         "dpgicp_enable_stage_timing": (C.c_int, [vp, i32]),
         "dpgicp_last_run_stage_ms": (C.c_int, [vp, C.POINTER(C.c_float * 8), C.POINTER(i32)]),
+        "dpgicp_run_range": (C.c_int, [vp, PP, i64, i64]),
+        "dpgicp_fetch_results_range": (C.c_int, [vp, vp, i64, i64]),
+        "dpgicp_gather_fetch_range": (C.c_int, [vp, vp, i64, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)      # AttributeError if the symbol is not exported

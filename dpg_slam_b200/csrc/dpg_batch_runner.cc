@@ -13,6 +13,12 @@
  *   per scan: float pose_est[3] (x, y, theta of base_link); int32 pass; float ranges[n_beams]
  * Output: one JSON line with counts, timings and result statistics; --out FILE writes the records
  * (src, tgt, tx, ty, theta, cov[9], status) as CSV for the pose-graph side.
+ *
+ * --gpus N (devices 0..N-1) or --devices a,b,... runs the batch on several GPUs from this one process
+ * (dpgicp_shim::MultiGpuScanMatcher): store and node table replicated, the pair list enumerated on every device with
+ * its round-robin shard kept, records gathered into device a's buffer by peer stores.  The CSV is identical for any N.
+ * --caller online enumerates the pairs of one updatePoseGraphObsConstraints call for the newest node instead of a
+ * whole reoptimize().
  */
 #include <chrono>
 #include <cmath>
@@ -151,6 +157,8 @@ void make_synthetic(const std::string &kind, int n_scans, int n_beams, int passe
 int main(int argc, char **argv) {
   std::string synthetic = "corridor", log_in, log_out, csv_out;
   int n_scans = 501, n_beams = 1081, passes = 1, device = 0;
+  std::vector<int> devices;
+  int32_t caller = DPGICP_ENUM_REOPTIMIZE;
   bool successive_only = false;
   uint64_t seed = 2;
   dpgicp_params params;
@@ -171,6 +179,14 @@ int main(int argc, char **argv) {
     else if (a == "--passes") passes = std::atoi(next("--passes"));
     else if (a == "--seed") seed = (uint64_t)std::atoll(next("--seed"));
     else if (a == "--device") device = std::atoi(next("--device"));
+    else if (a == "--gpus") { const int g = std::atoi(next("--gpus")); devices.clear(); for (int d = 0; d < g; ++d) devices.push_back(d); }
+    else if (a == "--devices") {
+      devices.clear();
+      for (const char *q = next("--devices"); *q;) { devices.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+    }
+    else if (a == "--caller") { const std::string c = next("--caller"); caller = c == "online" ? DPGICP_ENUM_ONLINE : DPGICP_ENUM_REOPTIMIZE; }
+    else if (a == "--outlier-mode") params.outlier_mode = std::atoi(next("--outlier-mode"));
+    else if (a == "--outlier-param") params.outlier_param = std::atof(next("--outlier-param"));
     else if (a == "--divisor") params.downsample_divisor = std::atoi(next("--divisor"));
     else if (a == "--cov-mode") params.cov_mode = std::atoi(next("--cov-mode"));
     else if (a == "--metric") params.metric = std::atoi(next("--metric"));
@@ -183,7 +199,8 @@ int main(int argc, char **argv) {
       std::fprintf(stderr,
                    "usage: dpg_batch_runner [--synthetic corridor|office | --log FILE] [--scans N] [--beams N] [--passes N]\n"
                    "         [--seed S] [--divisor D] [--cov-mode 0|1|2] [--metric 0|1] [--search 0|1|2] [--window W] [--successive-only]\n"
-                   "         [--same-pass-radius R] [--other-pass-radius R] [--write-log FILE] [--out FILE.csv] [--device K]\n");
+                   "         [--same-pass-radius R] [--other-pass-radius R] [--write-log FILE] [--out FILE.csv] [--device K]\n"
+                   "         [--gpus N | --devices a,b,...] [--caller reoptimize|online] [--outlier-mode 0|1|2 --outlier-param X]\n");
       return a == "--help" ? 0 : 2;
     }
   }
@@ -197,20 +214,34 @@ int main(int argc, char **argv) {
   if (!log_out.empty() && !write_log(log_out.c_str(), L)) { std::fprintf(stderr, "cannot write %s\n", log_out.c_str()); return 1; }
 
   try {
-    dpgicp_shim::ScanMatcher sm(device);
-    sm.params() = params;
-    const double t0 = now_s();
-    sm.uploadRanges(L.ranges, L.n_scans, L.n_beams, L.angle_min, L.angle_max, L.range_max, L.lx, L.ly, L.lt);
-    const double t1 = now_s();
     std::vector<int32_t> src, tgt;
+    std::vector<dpgicp_result> res;
+    double t0, t1, t2, t3;
+    if (devices.empty()) devices.push_back(device);
     if (successive_only) {
+      dpgicp_shim::ScanMatcher sm(devices[0]);
+      sm.params() = params;
+      t0 = now_s();
+      sm.uploadRanges(L.ranges, L.n_scans, L.n_beams, L.angle_min, L.angle_max, L.range_max, L.lx, L.ly, L.lt);
+      t1 = now_s();
       for (int i = 1; i < L.n_scans; ++i) { src.push_back(i); tgt.push_back(i - 1); }
+      t2 = now_s();
+      res = sm.runIcpBatch(L.est, src, tgt);
+      t3 = now_s();
     } else {
-      sm.enumeratePairs(L.est, L.pass, r_same, r_other, src, tgt);
+      /* the callers' form: nodes in, pair list enumerated and kept on the device(s), records gathered back */
+      dpgicp_shim::MultiGpuScanMatcher sm(devices);
+      sm.params() = params;
+      t0 = now_s();
+      sm.uploadRanges(L.ranges, L.n_scans, L.n_beams, L.angle_min, L.angle_max, L.range_max, L.lx, L.ly, L.lt);
+      t1 = now_s();
+      sm.setNodes(L.est, L.pass);
+      sm.enumeratePairs(caller, r_same, r_other);
+      t2 = now_s();
+      res = sm.runIcpBatch();
+      t3 = now_s();
+      sm.pairs(src, tgt);
     }
-    const double t2 = now_s();
-    std::vector<dpgicp_result> res = sm.runIcpBatch(L.est, src, tgt);
-    const double t3 = now_s();
     size_t converged = 0, singular = 0;
     double it_sum = 0;
     for (const dpgicp_result &r : res) {
@@ -230,10 +261,10 @@ int main(int argc, char **argv) {
       }
       std::fclose(f);
     }
-    std::printf("{\"scans\": %d, \"beams\": %d, \"pairs\": %zu, \"converged\": %zu, \"cov_singular\": %zu, "
+    std::printf("{\"scans\": %d, \"beams\": %d, \"gpus\": %zu, \"pairs\": %zu, \"converged\": %zu, \"cov_singular\": %zu, "
                 "\"mean_iterations\": %.2f, \"upload_s\": %.6f, \"enumerate_s\": %.6f, \"icp_cov_s\": %.6f, "
                 "\"pairs_per_s\": %.1f}\n",
-                L.n_scans, L.n_beams, res.size(), converged, singular, res.empty() ? 0.0 : it_sum / (double)res.size(),
+                L.n_scans, L.n_beams, devices.size(), res.size(), converged, singular, res.empty() ? 0.0 : it_sum / (double)res.size(),
                 t1 - t0, t2 - t1, t3 - t2, res.empty() ? 0.0 : (double)res.size() / (t3 - t2));
   } catch (const std::exception &e) {
     std::fprintf(stderr, "dpg_batch_runner: %s\n", e.what());

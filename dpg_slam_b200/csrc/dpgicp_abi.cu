@@ -264,7 +264,8 @@ int balanced_warps(int tiles, int target, int csize = 1) {
 }
 
 int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_params *p, int32_t *corr_out,
-               float *corr_d2, const int32_t *corr_seed = nullptr, int32_t *corr_nn_out = nullptr) {
+               float *corr_d2, const int32_t *corr_seed = nullptr, int32_t *corr_nn_out = nullptr, int64_t first = 0,
+               int64_t count = -1) {
   NvtxRange range("dpgicp: ICP + covariance stage chain");
   const int div = p->downsample_divisor;
   int n_max = (st.max_count + div - 1) / div;
@@ -276,11 +277,14 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   kp.store.count = (const int32_t *)st.count.p;
   kp.store.pitch = st.pitch;
   kp.store.n_scans = st.n_scans;
-  kp.tasks = (const PairTask *)b.tasks.p;
-  kp.order = b.has_order ? (const long long *)b.order.p : nullptr;
-  kp.results = (dpgicp_result *)b.results.p;
+  if (count < 0) count = b.n_pairs - first;
+  const bool whole = first == 0 && count == b.n_pairs;
+  kp.tasks = (const PairTask *)b.tasks.p + first;
+  kp.order = (b.has_order && whole) ? (const long long *)b.order.p : nullptr;
+  kp.results = (dpgicp_result *)b.results.p + first;
+  kp.pair_base = first;
   kp.counters = ctx->d_queue + 8;
-  kp.n_pairs = b.n_pairs;
+  kp.n_pairs = count;
   kp.n_cap = n_cap;
   kp.max_iterations = p->max_iterations;
   kp.use_reciprocal = p->use_reciprocal;
@@ -348,7 +352,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   if (n_stages > 1) {
     /* every stage can suspend at most one pair per CTA: size the state slots for stage 0's grid */
     int g0 = -1;
-    int rc = launch_stage(ctx, search, shapes[0].warps, shapes[0].csize, kp, smem, b.n_pairs, &g0);
+    int rc = launch_stage(ctx, search, shapes[0].warps, shapes[0].csize, kp, smem, count, &g0);
     if (rc) return rc;
     for (int k = 0; k < 2; ++k) {
       if ((rc = reserve(ctx, ctx->state[k], (size_t)g0 * (size_t)kp.slot_bytes))) return rc;
@@ -382,7 +386,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue + 6 + (sidx & 1), 0, sizeof(unsigned long long), ctx->stream));
     }
     int grid = 0;
-    const int64_t max_items = sidx == 0 ? b.n_pairs : (int64_t)grid_prev;
+    const int64_t max_items = sidx == 0 ? count : (int64_t)grid_prev;
     int rc = launch_stage(ctx, search, shapes[sidx].warps, shapes[sidx].csize, ks, smem, max_items, &grid);
     if (rc) return rc;
     grid_prev = grid;
@@ -523,27 +527,56 @@ int gather_close(dpgicp_ctx *ctx) {
   return DPGICP_OK;
 }
 
-/* host repack of an arbitrary-stride cloud into packed float2 */
-void pack_host(const void *pts, int n, size_t stride, std::vector<float> &out) {
-  out.resize((size_t)std::max(n, 0) * 2);
-  const unsigned char *b = (const unsigned char *)pts;
-  for (int k = 0; k < n; ++k) {
-    const float *f = (const float *)(b + (size_t)k * stride);
-    out[2 * k] = f[0]; out[2 * k + 1] = f[1];
-  }
-}
-
+/* The two clouds of a single-pair call (runIcp / calculate_ICP_COV shapes) as a two-row scratch store.  This is the
+ * latency path: the rows are laid out on the host in a page-locked buffer (range check included — the counts are
+ * known, so nothing has to come back from the device) and go up in one asynchronous copy; no kernel, no
+ * synchronisation. */
 int two_cloud_store(dpgicp_ctx *ctx, const void *a, int na, const void *b, int nb, size_t stride) {
   if (na < 0 || nb < 0 || (na > 0 && !a) || (nb > 0 && !b)) return fail(ctx, DPGICP_E_INVALID, "bad cloud arguments");
   if (stride < 8 || (stride % 4) != 0) return fail(ctx, DPGICP_E_INVALID, "stride_bytes must be >= 8 and a multiple of 4");
-  std::vector<float> pa, pb;
-  pack_host(a, na, stride, pa);
-  pack_host(b, nb, stride, pb);
-  pa.insert(pa.end(), pb.begin(), pb.end());
-  const int64_t off[3] = {0, na, (int64_t)na + nb};
-  return upload_scans_into(ctx, ctx->scratch_store, pa.data(), 8, off, 2);
+  if (na > DPGICP_MAX_POINTS || nb > DPGICP_MAX_POINTS) return fail(ctx, DPGICP_E_TOOBIG, "a scan has more than DPGICP_MAX_POINTS points");
+  Store &st = ctx->scratch_store;
+  const int pitch = std::max(2, (std::max(na, nb) + 1) & ~1);
+  const size_t row_bytes = sizeof(float2) * (size_t)pitch, blob = 2 * row_bytes + 16;
+  if (blob > ctx->h_pair_cap) {
+    if (ctx->h_pair) { CU_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->h_pair); }
+    ctx->h_pair = nullptr; ctx->h_pair_cap = 0;
+    CU_TRY(ctx, cudaMallocHost(&ctx->h_pair, blob));
+    ctx->h_pair_cap = blob;
+  } else {
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));       /* a previous call's copy out of the buffer (already done: every
+                                                            * single-pair call ends with a synchronisation) */
+  }
+  float *rows = (float *)ctx->h_pair;
+  const void *src[2] = {a, b};
+  const int cnt[2] = {na, nb};
+  for (int r = 0; r < 2; ++r) {
+    float *row = rows + (size_t)r * pitch * 2;
+    const unsigned char *p = (const unsigned char *)src[r];
+    for (int k = 0; k < cnt[r]; ++k) {
+      const float *f = (const float *)(p + (size_t)k * stride);
+      const float x = f[0], y = f[1];
+      if (!(std::fabs(x) <= DPGICP_MAX_ABS_COORD) || !(std::fabs(y) <= DPGICP_MAX_ABS_COORD)) {
+        st.n_scans = 0;
+        return fail(ctx, DPGICP_E_RANGE, "scan store holds a non-finite point or |coordinate| > DPGICP_MAX_ABS_COORD");
+      }
+      row[2 * k] = x; row[2 * k + 1] = y;
+    }
+    std::memset(row + 2 * (size_t)cnt[r], 0, sizeof(float) * 2 * (size_t)(pitch - cnt[r]));
+  }
+  int32_t *h_cnt = (int32_t *)((char *)ctx->h_pair + 2 * row_bytes);
+  h_cnt[0] = na; h_cnt[1] = nb;
+  int rc;
+  if ((rc = reserve(ctx, st.rows, 2 * row_bytes))) return rc;
+  if ((rc = reserve(ctx, st.count, 2 * sizeof(int32_t)))) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(st.rows.p, rows, 2 * row_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(st.count.p, h_cnt, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  st.pitch = pitch;
+  st.n_scans = 2;
+  st.max_count = std::max(na, nb);
+  st.h_count.assign({na, nb});
+  return DPGICP_OK;
 }
-
 
 /* node estimates -> device, plus the index-order box hierarchy the enumeration walks */
 int set_nodes_impl(dpgicp_ctx *ctx, const float *pose, const int32_t *pass, int32_t n, bool pose_is_xy) {
@@ -991,6 +1024,43 @@ int dpgicp_run(dpgicp_ctx *ctx, const dpgicp_params *params) {
   return launch_icp(ctx, ctx->store, ctx->batch, params, nullptr, nullptr);
 }
 
+int dpgicp_run_range(dpgicp_ctx *ctx, const dpgicp_params *params, int64_t first, int64_t count) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = check_params(ctx, params);
+  if (rc) return rc;
+  if (first < 0 || count < 0 || first + count > ctx->batch.n_pairs) return fail(ctx, DPGICP_E_INVALID, "pair range outside the batch");
+  if (count == 0) return DPGICP_OK;
+  if (ctx->store.n_scans <= 0) return fail(ctx, DPGICP_E_STATE, "no scans uploaded");
+  if (ctx->batch.max_scan >= ctx->store.n_scans)
+    return fail(ctx, DPGICP_E_STATE, "the enumerated pair list refers to nodes without a scan in the store (node k owns scan k)");
+  return launch_icp(ctx, ctx->store, ctx->batch, params, nullptr, nullptr, nullptr, nullptr, first, count);
+}
+
+int dpgicp_fetch_results_range(dpgicp_ctx *ctx, dpgicp_result *out, int64_t first, int64_t count) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (first < 0 || count < 0 || first + count > ctx->batch.n_pairs || (count > 0 && !out)) return fail(ctx, DPGICP_E_INVALID, "bad fetch arguments");
+  if (count > 0)
+    CU_TRY(ctx, cudaMemcpyAsync(out, (const dpgicp_result *)ctx->batch.results.p + first, sizeof(dpgicp_result) * (size_t)count,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
+}
+
+int dpgicp_gather_fetch_range(dpgicp_ctx *ctx, dpgicp_result *out, int64_t first, int64_t count) {
+  if (!ctx) return DPGICP_E_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (first < 0 || count < 0 || first + count > ctx->gather_n || (count > 0 && !out)) return fail(ctx, DPGICP_E_INVALID, "bad fetch arguments");
+  if (sizeof(dpgicp_result) * (size_t)(first + count) > ctx->gather.cap)
+    return fail(ctx, DPGICP_E_STATE, "this rank holds no gathered records (root-only gather: fetch from rank 0)");
+  if (count > 0)
+    CU_TRY(ctx, cudaMemcpyAsync(out, (const dpgicp_result *)ctx->gather.p + first, sizeof(dpgicp_result) * (size_t)count,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return DPGICP_OK;
+}
+
 int dpgicp_fetch_results(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n) {
   if (!ctx) return DPGICP_E_INVALID;
   NvtxRange range("dpgicp: fetch records");
@@ -1022,8 +1092,7 @@ int dpgicp_fetch_factors(dpgicp_ctx *ctx, dpgicp_factor *out, int64_t n) {
   return DPGICP_OK;
 }
 
-int dpgicp_gather_export(dpgicp_ctx *ctx, int64_t n_global, unsigned char handle_out[DPGICP_IPC_HANDLE_BYTES]) {
-  if (!ctx || !handle_out || n_global < 0) return DPGICP_E_INVALID;
+static int gather_export_impl(dpgicp_ctx *ctx, int64_t n_global, int64_t n_alloc, unsigned char *handle_out) {
   static_assert(sizeof(cudaIpcMemHandle_t) == DPGICP_IPC_HANDLE_BYTES, "IPC handle size");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1032,7 +1101,7 @@ int dpgicp_gather_export(dpgicp_ctx *ctx, int64_t n_global, unsigned char handle
   /* a dedicated cudaMalloc allocation (IPC handles cover whole allocations) */
   release(ctx->gather);
   int rc;
-  if ((rc = reserve(ctx, ctx->gather, sizeof(dpgicp_result) * (size_t)std::max<int64_t>(n_global, 1)))) return rc;
+  if ((rc = reserve(ctx, ctx->gather, sizeof(dpgicp_result) * (size_t)std::max<int64_t>(n_alloc, 1)))) return rc;
   CU_TRY(ctx, cudaMemsetAsync(ctx->gather.p, 0, ctx->gather.cap, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->gather_n = n_global;
@@ -1040,6 +1109,16 @@ int dpgicp_gather_export(dpgicp_ctx *ctx, int64_t n_global, unsigned char handle
   CU_TRY(ctx, cudaIpcGetMemHandle(&h, ctx->gather.p));
   std::memcpy(handle_out, &h, sizeof(h));
   return DPGICP_OK;
+}
+
+int dpgicp_gather_export(dpgicp_ctx *ctx, int64_t n_global, unsigned char handle_out[DPGICP_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle_out || n_global < 0) return DPGICP_E_INVALID;
+  return gather_export_impl(ctx, n_global, n_global, handle_out);
+}
+
+int dpgicp_gather_declare(dpgicp_ctx *ctx, int64_t n_global, unsigned char handle_out[DPGICP_IPC_HANDLE_BYTES]) {
+  if (!ctx || !handle_out || n_global < 0) return DPGICP_E_INVALID;
+  return gather_export_impl(ctx, n_global, 1, handle_out);
 }
 
 int dpgicp_gather_attach(dpgicp_ctx *ctx, const unsigned char *handles, int32_t world, int32_t rank) {
@@ -1119,6 +1198,8 @@ int dpgicp_gather_fetch(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n) {
   if (!ctx) return DPGICP_E_INVALID;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if (n < 0 || n > ctx->gather_n || (n > 0 && !out)) return fail(ctx, DPGICP_E_INVALID, "bad fetch arguments");
+  if (sizeof(dpgicp_result) * (size_t)n > ctx->gather.cap)
+    return fail(ctx, DPGICP_E_STATE, "this rank holds no gathered records (root-only gather: fetch from rank 0)");
   if (n > 0)
     CU_TRY(ctx, cudaMemcpyAsync(out, ctx->gather.p, sizeof(dpgicp_result) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

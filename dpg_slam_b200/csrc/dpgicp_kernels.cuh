@@ -126,6 +126,7 @@ struct KernelParams {
   dpgicp_result *gather_peer[DPGICP_MAX_GATHER_RANKS];
   int32_t gather_world, gather_rank;
   int32_t gather_fanout;              /* buffers written: gather_world (every rank's) or 1 (rank 0's only)        */
+  long long pair_base;                /* dpgicp_run_range: tasks / results point at local pair pair_base of the batch */
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -1383,7 +1384,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       if (P.out_count != nullptr) atomicAdd(P.finished, 1ull);
       if (P.gather_world > 1) {
         /* fused gather: seven 16-byte stores per peer, straight into every rank's buffer at the global slot */
-        const long long slot = (long long)P.gather_rank + pair * (long long)P.gather_world;
+        const long long slot = (long long)P.gather_rank + (P.pair_base + pair) * (long long)P.gather_world;
         const int4 *src = reinterpret_cast<const int4 *>(&r);
         for (int g = 0; g < P.gather_fanout; ++g) {
           int4 *dst = reinterpret_cast<int4 *>(P.gather_peer[g] + slot);

@@ -15,6 +15,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 static inline uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
@@ -147,9 +150,11 @@ void dpgsynth_cast_scans(const float *segs, int nseg, const double *poses, int n
                          double noise_sigma, uint64_t seed, double laser_x, double laser_y,
                          int threads, float *ranges_out) {
   const float angle_inc = (float)(((double)(float)(angle_max - angle_min)) / ((double)n_beams - 1.0));
-  (void)threads;
 #ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 8)
+  if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 8) num_threads(threads)
+#else
+  (void)threads;
 #endif
   for (int s = 0; s < n_scans; ++s) {
     const double px = poses[3 * s], py = poses[3 * s + 1], th = poses[3 * s + 2];

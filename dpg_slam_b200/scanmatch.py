@@ -175,6 +175,26 @@ class ScanMatcher:
         """Launch the resident batch asynchronously on the context's stream."""
         self._check(self._lib.dpgicp_run(self._h, C.byref(params)))
 
+    def run_range(self, params: Params, first: int, count: int):
+        """Pairs [first, first + count) of the resident list (asynchronous)."""
+        self._check(self._lib.dpgicp_run_range(self._h, C.byref(params), first, count))
+
+    def fetch_results_range(self, first: int, count: int, host_ptr: Optional[int] = None) -> Optional[np.ndarray]:
+        if host_ptr is not None:
+            self._check(self._lib.dpgicp_fetch_results_range(self._h, C.c_void_p(host_ptr), first, count))
+            return None
+        out = np.zeros(count, RESULT_DTYPE)
+        self._check(self._lib.dpgicp_fetch_results_range(self._h, out.ctypes.data, first, count))
+        return out
+
+    def gather_fetch_range(self, first: int, count: int, host_ptr: Optional[int] = None) -> Optional[np.ndarray]:
+        if host_ptr is not None:
+            self._check(self._lib.dpgicp_gather_fetch_range(self._h, C.c_void_p(host_ptr), first, count))
+            return None
+        out = np.zeros(count, RESULT_DTYPE)
+        self._check(self._lib.dpgicp_gather_fetch_range(self._h, out.ctypes.data, first, count))
+        return out
+
     def fetch_results(self, n: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
         n = self._n_pairs if n is None else n
         if out is None:
@@ -203,6 +223,12 @@ class ScanMatcher:
         """Allocate this rank's buffer for the WHOLE batch's records; returns its 64-byte CUDA IPC handle."""
         h = (C.c_ubyte * _abi.IPC_HANDLE_BYTES)()
         self._check(self._lib.dpgicp_gather_export(self._h, n_global_pairs, C.byref(h)))
+        return bytes(h)
+
+    def gather_declare(self, n_global_pairs: int) -> bytes:
+        """Root-only gathers: a rank other than 0 only declares the global batch size (placeholder buffer)."""
+        h = (C.c_ubyte * _abi.IPC_HANDLE_BYTES)()
+        self._check(self._lib.dpgicp_gather_declare(self._h, n_global_pairs, C.byref(h)))
         return bytes(h)
 
     def gather_attach(self, handles, rank: int):

@@ -155,16 +155,20 @@ class ShardedScanMatcher:
         return self._recv
 
     # ---- gather fused into the kernel: no collective on the data path ----------------------------------------
-    def attach_fused_gather(self, n_global_pairs: int) -> bool:
+    def attach_fused_gather(self, n_global_pairs: int, root_only: bool = False) -> bool:
         """Exchange CUDA IPC handles of per-rank whole-batch buffers once; afterwards every ``run`` writes its
-        records straight into all ranks' buffers from the kernel epilogue (peer stores over NVLink).  Returns
-        False — on EVERY rank, after an agreement round — when some rank could not map a peer's buffer (no
-        peer access between the devices); the caller then gathers with :meth:`gather_device` (NCCL)."""
+        records straight into all ranks' buffers from the kernel epilogue (peer stores over NVLink) — or, with
+        ``root_only``, into rank 0's buffer alone (what ONE host-side pose-graph update needs; the other ranks then
+        allocate nothing).  Returns False — on EVERY rank, after an agreement round — when some rank could not map a
+        peer's buffer (no peer access between the devices); the caller then gathers with :meth:`gather_device` (NCCL)."""
         import torch
         import torch.distributed as dist
         ok = 1
+        self._root_only = bool(root_only)
         try:
-            mine = self.sm.gather_export(n_global_pairs)
+            self.sm.gather_set_root_only(root_only)
+            mine = (self.sm.gather_declare(n_global_pairs) if (root_only and self.rank != 0)
+                    else self.sm.gather_export(n_global_pairs))
         except Exception:
             mine, ok = b"\0" * 64, 0
         handles = [None] * self.world
@@ -194,13 +198,20 @@ class ShardedScanMatcher:
         self.sm.gather_detach()
         self._fused = 0
 
-    def fused_records(self) -> np.ndarray:
-        """All records in global pair order from this rank's own buffer.  Synchronises this rank's stream and
-        then all ranks (a peer's stores are complete once its kernel has finished)."""
+    def fused_records(self, n_pairs: Optional[int] = None) -> Optional[np.ndarray]:
+        """All records in global pair order from this rank's own buffer (rank 0's only after a root-only attach: the
+        other ranks get None).  Synchronises this rank's stream and then all ranks (a peer's stores are complete once
+        its kernel has finished); a second barrier after the copy keeps a faster rank's NEXT run from storing new
+        records into a buffer that is still being read."""
         import torch.distributed as dist
+        n = self.n_pairs if n_pairs is None else int(n_pairs)
         self.sm.synchronize()
         dist.barrier(group=self.group)
-        return self.sm.gather_fetch(self.n_pairs)
+        out = None
+        if not getattr(self, "_root_only", False) or self.rank == 0:
+            out = self.sm.gather_fetch(n)
+        dist.barrier(group=self.group)
+        return out
 
     def gather(self) -> np.ndarray:
         """All ``n_pairs`` records in global pair order, on the host, on every rank."""

@@ -107,6 +107,17 @@ def world_office(size=40.0, n_boxes=60, seed=3, variant=0, moved_fraction=0.05) 
     return _segs(_synth().dpgsynth_world_office, size, n_boxes, seed, variant, moved_fraction)
 
 
+def _cast_threads() -> int:
+    """Host threads for the ray caster: all cores this process may use, shared between the ranks of a torch.distributed
+    launch (which sets OMP_NUM_THREADS=1 — input generation is not the measured path and should not take minutes)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    return max(1, n // world)
+
+
 def cast_scans(segs: np.ndarray, poses: np.ndarray, scanner: Scanner, seed: int) -> np.ndarray:
     segs = np.ascontiguousarray(segs, np.float32)
     poses = np.ascontiguousarray(poses, np.float64)
@@ -114,7 +125,7 @@ def cast_scans(segs: np.ndarray, poses: np.ndarray, scanner: Scanner, seed: int)
     _synth().dpgsynth_cast_scans(segs.ctypes.data, segs.shape[0], poses.ctypes.data, poses.shape[0],
                                  scanner.n_beams, scanner.angle_min, scanner.angle_max,
                                  scanner.range_min, scanner.range_max, scanner.noise_sigma, seed,
-                                 scanner.laser_x, scanner.laser_y, 0, out.ctypes.data)
+                                 scanner.laser_x, scanner.laser_y, _cast_threads(), out.ctypes.data)
     return out
 
 

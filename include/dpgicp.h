@@ -214,6 +214,11 @@ int  dpgicp_run(dpgicp_ctx *ctx, const dpgicp_params *params);         /* async 
  * it (tested).  NULL clears the hint; set_pairs clears it too.                                                  */
 int  dpgicp_set_pair_cost_hints(dpgicp_ctx *ctx, const float *hints, int64_t n_pairs);
 int  dpgicp_fetch_results(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n_pairs); /* D2H + sync   */
+/* Part of the resident pair list: pairs [first, first + count) (asynchronous like dpgicp_run; records, fused-gather
+ * slots and factors keep the indices of the whole list).  Lets a caller stream a very large enumerated list through
+ * the device in slices, or warm up on a prefix.  The *_range fetches copy the matching records.                 */
+int  dpgicp_run_range(dpgicp_ctx *ctx, const dpgicp_params *params, int64_t first, int64_t count);
+int  dpgicp_fetch_results_range(dpgicp_ctx *ctx, dpgicp_result *out, int64_t first, int64_t count);
 /* Records of the last dpgicp_run turned into pose-graph factors on the device (one per pair, pair order). */
 int  dpgicp_fetch_factors(dpgicp_ctx *ctx, dpgicp_factor *out, int64_t n_pairs);
 /* device address of the record array written by dpgicp_run (n_pairs * sizeof(dpgicp_result));
@@ -229,11 +234,15 @@ int  dpgicp_results_device_ptr(dpgicp_ctx *ctx, void **out_ptr, int64_t *out_n_p
 #define DPGICP_IPC_HANDLE_BYTES   64
 #define DPGICP_MAX_GATHER_RANKS   16
 int  dpgicp_gather_export(dpgicp_ctx *ctx, int64_t n_global_pairs, unsigned char handle_out[DPGICP_IPC_HANDLE_BYTES]);
+/* root-only gathers (dpgicp_gather_set_root_only): ranks other than 0 receive nothing, so they only declare the size of
+ * the global batch (a one-record placeholder allocation backs the handle)                                   */
+int  dpgicp_gather_declare(dpgicp_ctx *ctx, int64_t n_global_pairs, unsigned char handle_out[DPGICP_IPC_HANDLE_BYTES]);
 /* handles = world * 64 bytes in rank order (this rank's own entry is ignored and may be anything) */
 int  dpgicp_gather_attach(dpgicp_ctx *ctx, const unsigned char *handles, int32_t world, int32_t rank);
 int  dpgicp_gather_detach(dpgicp_ctx *ctx);
 /* copy the first n records of this rank's gather buffer to the host (caller has synchronised all ranks) */
 int  dpgicp_gather_fetch(dpgicp_ctx *ctx, dpgicp_result *out, int64_t n_global_pairs);
+int  dpgicp_gather_fetch_range(dpgicp_ctx *ctx, dpgicp_result *out, int64_t first, int64_t count);
 int  dpgicp_gather_device_ptr(dpgicp_ctx *ctx, void **out_ptr, int64_t *out_n_global_pairs);
 
 /* executed-work counters of the last dpgicp_run, summed over pairs (after synchronisation):

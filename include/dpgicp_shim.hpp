@@ -18,8 +18,10 @@
 #define DPGICP_SHIM_HPP
 
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -146,6 +148,115 @@ class ScanMatcher {
     if (rc != DPGICP_OK) throw std::runtime_error(std::string(what) + ": " + last_error());
   }
   dpgicp_ctx *ctx_ = nullptr;
+  dpgicp_params params_{};
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * The batch form of the two callers on G GPUs of one box, driven from ONE host process in C++ (the role of the
+ * reference's data runner, src/runner/dpg_data_runner_main.cc:95-128, and of DpgSLAM::reoptimize /
+ * updatePoseGraphObsConstraints, dpg_slam.cc:35-120, 255-314).  One dpgicp context per device; the scan store and
+ * the node table are replicated; the pair list is enumerated ON every device, each keeping its round-robin shard
+ * (global pair k -> context k % G); the records are gathered by peer stores from the kernels' epilogues into
+ * context 0's buffer (dpgicp_gather_attach_local, no collective, no host interleave).  The same device may be listed
+ * more than once (two contexts on one GPU), which is how a single-GPU box exercises this path.
+ * ---------------------------------------------------------------------------------------------- */
+class MultiGpuScanMatcher {
+ public:
+  explicit MultiGpuScanMatcher(const std::vector<int> &devices) {
+    if (devices.empty() || devices.size() > DPGICP_MAX_GATHER_RANKS) throw std::runtime_error("MultiGpuScanMatcher: 1..16 devices");
+    for (int d : devices) {
+      dpgicp_ctx *c = nullptr;
+      if (dpgicp_create(d, &c) != DPGICP_OK) {
+        const std::string msg = dpgicp_last_error(nullptr);
+        for (dpgicp_ctx *q : ctx_) dpgicp_destroy(q);
+        throw std::runtime_error("dpgicp_create(device " + std::to_string(d) + "): " + msg);
+      }
+      ctx_.push_back(c);
+    }
+    dpgicp_default_params(&params_);
+  }
+  ~MultiGpuScanMatcher() {
+    for (dpgicp_ctx *c : ctx_) dpgicp_gather_detach(c);
+    for (dpgicp_ctx *c : ctx_) dpgicp_destroy(c);
+  }
+  MultiGpuScanMatcher(const MultiGpuScanMatcher &) = delete;
+  MultiGpuScanMatcher &operator=(const MultiGpuScanMatcher &) = delete;
+
+  dpgicp_params &params() { return params_; }
+  int world() const { return (int)ctx_.size(); }
+  dpgicp_ctx *ctx(int r) { return ctx_[(size_t)r]; }
+
+  /* replicate the scan store (raw ranges, converted on each device) */
+  void uploadRanges(const std::vector<float> &ranges, int n_scans, int n_beams, float angle_min, float angle_max,
+                    float range_max, float lx = 0.2f, float ly = 0.0f, float ltheta = 0.0f) {
+    each([&](int r) {
+      return dpgicp_upload_ranges(ctx_[(size_t)r], ranges.data(), n_scans, n_beams, angle_min, angle_max, range_max, lx, ly, ltheta);
+    }, "dpgicp_upload_ranges");
+  }
+  /* node estimates (DpgNode::getEstimatedPosition) and pass numbers; node k owns scan k */
+  void setNodes(const std::vector<Pose2f> &poses, const std::vector<int32_t> &pass) {
+    std::vector<float> flat(poses.size() * 3);
+    for (size_t i = 0; i < poses.size(); ++i) { flat[3 * i] = poses[i].x; flat[3 * i + 1] = poses[i].y; flat[3 * i + 2] = poses[i].theta; }
+    each([&](int r) { return dpgicp_set_nodes(ctx_[(size_t)r], flat.data(), pass.data(), (int32_t)poses.size()); }, "dpgicp_set_nodes");
+  }
+  /* the caller's pair list (DPGICP_ENUM_REOPTIMIZE / _ONLINE) built on every device; returns the global pair count */
+  int64_t enumeratePairs(int32_t mode, float same_pass_radius, float other_pass_radius) {
+    std::vector<int64_t> total(ctx_.size(), 0);
+    local_.assign(ctx_.size(), 0);
+    each([&](int r) {
+      return dpgicp_enumerate_pairs_device(ctx_[(size_t)r], mode, same_pass_radius, other_pass_radius, r, world(),
+                                           &total[(size_t)r], &local_[(size_t)r]);
+    }, "dpgicp_enumerate_pairs_device");
+    n_total_ = total[0];
+    return n_total_;
+  }
+  /* align every pair: all devices run concurrently; records land in context 0's gather buffer in global order */
+  std::vector<dpgicp_result> runIcpBatch() {
+    std::vector<dpgicp_result> out((size_t)n_total_);
+    if (n_total_ == 0) return out;
+    if (world() > 1 && dpgicp_gather_attach_local(ctx_.data(), world(), n_total_, /*root_only=*/1) != DPGICP_OK)
+      throw std::runtime_error(std::string("dpgicp_gather_attach_local: ") + first_error());
+    for (int r = 0; r < world(); ++r)                      /* dpgicp_run only launches: one thread starts them all */
+      if (dpgicp_run(ctx_[(size_t)r], &params_) != DPGICP_OK) throw std::runtime_error(std::string("dpgicp_run: ") + dpgicp_last_error(ctx_[(size_t)r]));
+    for (int r = 0; r < world(); ++r)
+      if (dpgicp_synchronize(ctx_[(size_t)r]) != DPGICP_OK) throw std::runtime_error(std::string("dpgicp_synchronize: ") + dpgicp_last_error(ctx_[(size_t)r]));
+    const int rc = world() > 1 ? dpgicp_gather_fetch(ctx_[0], out.data(), n_total_) : dpgicp_fetch_results(ctx_[0], out.data(), n_total_);
+    if (rc != DPGICP_OK) throw std::runtime_error(std::string("fetch records: ") + dpgicp_last_error(ctx_[0]));
+    return out;
+  }
+  /* the global pair list (source, target node per pair) in the reference's loop order */
+  void pairs(std::vector<int32_t> &src, std::vector<int32_t> &tgt) {
+    src.assign((size_t)n_total_, 0); tgt.assign((size_t)n_total_, 0);
+    for (int r = 0; r < world(); ++r) {
+      const int64_t n = local_[(size_t)r];
+      std::vector<int32_t> s((size_t)n), t((size_t)n);
+      if (dpgicp_fetch_pairs(ctx_[(size_t)r], s.data(), t.data(), nullptr, n) != DPGICP_OK)
+        throw std::runtime_error(std::string("dpgicp_fetch_pairs: ") + dpgicp_last_error(ctx_[(size_t)r]));
+      for (int64_t k = 0; k < n; ++k) { src[(size_t)(r + k * world())] = s[(size_t)k]; tgt[(size_t)(r + k * world())] = t[(size_t)k]; }
+    }
+  }
+
+ private:
+  /* the same host-side call on every context, one thread per context (a context is single-owner, contexts are independent) */
+  void each(const std::function<int(int)> &fn, const char *what) {
+    std::vector<int> rc(ctx_.size(), 0);
+    if (ctx_.size() == 1) {
+      rc[0] = fn(0);
+    } else {
+      std::vector<std::thread> th;
+      for (int r = 0; r < world(); ++r) th.emplace_back([&, r] { rc[(size_t)r] = fn(r); });
+      for (std::thread &t : th) t.join();
+    }
+    for (int r = 0; r < world(); ++r)
+      if (rc[(size_t)r] != DPGICP_OK) throw std::runtime_error(std::string(what) + " (context " + std::to_string(r) + "): " + dpgicp_last_error(ctx_[(size_t)r]));
+  }
+  const char *first_error() {
+    for (dpgicp_ctx *c : ctx_) if (dpgicp_last_error(c)[0]) return dpgicp_last_error(c);
+    return "";
+  }
+  std::vector<dpgicp_ctx *> ctx_;
+  std::vector<int64_t> local_;
+  int64_t n_total_ = 0;
   dpgicp_params params_{};
 };
 

@@ -1,0 +1,111 @@
+"""TEST-ONLY, independent emulation of what PCL's IterativeClosestPoint does with the reference's settings
+(reference call sites src/dpg_slam/dpg_slam.cc:404-416,445; parameters.h:146,159,173,201), written from
+SURVEY.md Appendix A.1-A.5 with NONE of the oracle's machinery: a kd-tree (scipy cKDTree, exact search) instead of
+grids or boxes, float32 3-D points with z = 0, float32 Umeyama through an SVD (numpy / LAPACK) instead of the planar
+closed form, float32 4x4 matrix products for `src' = step * src'` and `final = step * final`, float sums for the MSE,
+and PCL's DefaultConvergenceCriteria in PCL's order.  PCL itself is absent from this image, so this does not pin the
+ICP loop; it removes self-confirmation: the oracle (fixed-point moments, binary64 closed-form step, own tie rule) and
+this emulation share no code and no arithmetic shortcuts, and the test reports where they part.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.spatial import cKDTree
+
+F = np.float32
+
+
+def guess_matrix(guess) -> np.ndarray:
+    """dpg_slam.cc:374-378: Matrix4f from (dx, dy, dtheta); cos/sin of the float angle, stored as float."""
+    g = np.asarray(guess, F)
+    c, s = F(np.cos(np.float64(g[2]))), F(np.sin(np.float64(g[2])))
+    T = np.eye(4, dtype=F)
+    T[0, 0], T[0, 1], T[0, 3] = c, -s, g[0]
+    T[1, 0], T[1, 1], T[1, 3] = s, c, g[1]
+    return T
+
+
+def transform(T: np.ndarray, pts3: np.ndarray) -> np.ndarray:
+    """pcl::transformPointCloud with a Matrix4f: float32 throughout."""
+    R, t = T[:3, :3].astype(F), T[:3, 3].astype(F)
+    return (pts3.astype(F) @ R.T + t).astype(F)
+
+
+def umeyama_float32(src3: np.ndarray, dst3: np.ndarray) -> np.ndarray:
+    """Eigen::umeyama(src, dst, with_scaling = false) in float32, as TransformationEstimationSVD<.., float> calls it
+    (App. A.3-5): means, covariance (1/n) sum (dst - mu_d)(src - mu_s)^T, SVD, R = U diag(1, 1, +-1) V^T."""
+    n = F(src3.shape[0])
+    mu_s = (src3.sum(axis=0, dtype=F) / n).astype(F)
+    mu_d = (dst3.sum(axis=0, dtype=F) / n).astype(F)
+    sd, dd = (src3 - mu_s).astype(F), (dst3 - mu_d).astype(F)
+    sigma = ((dd.T @ sd) * (F(1.0) / n)).astype(F)
+    U, _, Vt = np.linalg.svd(sigma.astype(F))
+    S = np.ones(3, F)
+    if np.linalg.det(U.astype(np.float64)) * np.linalg.det(Vt.astype(np.float64)) < 0:
+        S[2] = F(-1.0)
+    R = ((U * S) @ Vt).astype(F)
+    T = np.eye(4, dtype=F)
+    T[:3, :3] = R
+    T[:3, 3] = (mu_d - R @ mu_s).astype(F)
+    return T
+
+
+def icp(src_xy, tgt_xy, guess, max_iterations=500, eps=5e-9, max_dist=0.6, reciprocal=True, trace=None):
+    """-> dict(T (4x4 float32), converged, iterations, stop, n_corr, mse).  stop in {"iterations", "transform",
+    "abs_mse", "no_correspondences"}.  ``trace`` (a list) receives (final BEFORE the pass as (c, s, tx, ty), K) per pass."""
+    src = np.zeros((len(src_xy), 3), F)
+    tgt = np.zeros((len(tgt_xy), 3), F)
+    if len(src_xy):
+        src[:, :2] = np.asarray(src_xy, F)
+    if len(tgt_xy):
+        tgt[:, :2] = np.asarray(tgt_xy, F)
+    final = guess_matrix(guess)                                         # A.2
+    cur = transform(final, src)
+    out = dict(T=final, converged=False, iterations=0, stop="no_correspondences", n_corr=0, mse=0.0)
+    if len(src) == 0 or len(tgt) == 0:
+        return out
+    tree_t = cKDTree(tgt.astype(np.float64))                            # A.1: target tree built once
+    max_d2 = np.float64(max_dist) * np.float64(max_dist)                # double threshold vs float distance (A.3-2)
+    mse_prev = np.finfo(np.float64).max
+    it = 0
+    while True:
+        _, j = tree_t.query(cur.astype(np.float64), k=1)
+        diff = (cur - tgt[j]).astype(F)
+        d2 = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1] + diff[:, 2] * diff[:, 2]).astype(F)   # FLANN L2_Simple
+        ok = ~(d2.astype(np.float64) > max_d2)
+        if reciprocal:
+            tree_s = cKDTree(cur.astype(np.float64))                    # rebuilt every iteration: the source moved
+            _, back = tree_s.query(tgt[j].astype(np.float64), k=1)
+            ok &= back == np.arange(len(cur))
+        idx = np.nonzero(ok)[0]
+        K = len(idx)
+        out["n_corr"] = K
+        if trace is not None:
+            trace.append((np.array([final[0, 0], final[1, 0], final[0, 3], final[1, 3]], F), K))
+        if K < 3:                                                       # A.3-4
+            out.update(converged=False, stop="no_correspondences", iterations=it, T=final)
+            return out
+        step = umeyama_float32(cur[idx], tgt[j[idx]])                   # A.3-5
+        cur = transform(step, cur)                                      # A.3-6
+        final = (step @ final).astype(F)
+        it += 1
+        mse = float(np.sum(d2[idx].astype(np.float64)) / np.float64(K))
+        out.update(T=final, iterations=it, mse=mse)
+        # A.5 DefaultConvergenceCriteria, in PCL's order
+        if it >= max_iterations:
+            out.update(converged=True, stop="iterations")
+            return out
+        cos_angle = 0.5 * (np.float64(step[0, 0]) + np.float64(step[1, 1]) + np.float64(step[2, 2]) - 1.0)
+        t2 = np.float64(step[0, 3]) ** 2 + np.float64(step[1, 3]) ** 2 + np.float64(step[2, 3]) ** 2
+        if cos_angle >= 1.0 - eps and t2 <= eps:
+            out.update(converged=True, stop="transform")
+            return out
+        if abs(mse - mse_prev) < 1e-12:
+            out.update(converged=True, stop="abs_mse")
+            return out
+        mse_prev = mse
+
+
+def pose_of(T: np.ndarray):
+    """dpg_slam.cc:434-439: (tx, ty, theta)"""
+    return float(T[0, 3]), float(T[1, 3]), float(np.arctan2(np.float64(T[1, 0]), np.float64(T[0, 0])))

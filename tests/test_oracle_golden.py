@@ -427,3 +427,95 @@ def test_projective_definition_on_unsorted_and_degenerate_clouds():
                 else:
                     d = [(np.float32(x - tgt[j, 0]) ** 2 + np.float32(y - tgt[j, 1]) ** 2, j) for j in cand]
                     assert c2[i] == min(d)[1], (n_s, n_t, i)
+
+
+# ---- tie rule, outlier rejectors, the online caller (ABI v3; defined by the oracle) ------------------------------------
+def test_sticky_tie_rule_prefers_the_previous_neighbour():
+    """Among exact ties the previous pass's neighbour wins, else the lowest index; a non-minimiser seed is ignored;
+    the reciprocal test keeps a pair unless a source point is STRICTLY closer (both askers of an exact tie are kept)."""
+    from dpg_slam_b200._abi import Params
+    tgt = np.array([(0, 0), (1, 0), (2, 0), (10, 10)], np.float32)
+    src = np.array([(0.5, 0), (1.5, 0), (0.25, 0)], np.float32)          # 0: ties targets 0/1, 1: ties 1/2, 2: nearest 0
+    p = Params.defaults(use_reciprocal=0)
+    k, corr, d2, nn = O.correspondences(src, tgt, p, prev_nn=[-1, -1, -1])
+    assert list(corr) == [0, 1, 0] and list(nn) == [0, 1, 0]            # no history: lowest index
+    k, corr, d2, nn = O.correspondences(src, tgt, p, prev_nn=[1, 2, 1])
+    assert list(corr) == [1, 2, 0] and list(nn) == [1, 2, 0]            # history among the minimisers wins; 1 is not one for point 2
+    k, corr, d2, nn = O.correspondences(src, tgt, p, prev_nn=[3, 0, 2])
+    assert list(corr) == [0, 1, 0]                                      # seeds that are not minimisers are ignored
+    # reciprocal, asker wins ties: source points 0 and 1 are both exactly 0.5 from target 1
+    src2 = np.array([(0.5, 0), (1.5, 0)], np.float32)
+    k, corr, _, _ = O.correspondences(src2, tgt[:3], Params.defaults(), prev_nn=[1, 1])
+    assert list(corr) == [1, 1] and k == 2
+    # ... but a strictly closer source point takes the target
+    src3 = np.array([(0.5, 0), (1.25, 0)], np.float32)
+    k, corr, _, _ = O.correspondences(src3, tgt[:3], Params.defaults(), prev_nn=[1, 1])
+    assert list(corr) == [-1, 1] and k == 1
+    # grid search == brute force with seeds too
+    rng = np.random.default_rng(5)
+    lat = np.stack([rng.integers(0, 9, 200) * 0.25, rng.integers(0, 9, 200) * 0.25], 1).astype(np.float32)
+    q = np.stack([rng.integers(0, 17, 150) * 0.125, rng.integers(0, 17, 150) * 0.125], 1).astype(np.float32)
+    prev = rng.integers(-1, 200, 150).astype(np.int32)
+    a = O.correspondences(q, lat, Params.defaults(), fast=0, prev_nn=prev)
+    b = O.correspondences(q, lat, Params.defaults(), fast=1, prev_nn=prev)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3]) and a[0] == b[0]
+
+
+def test_outlier_threshold_definitions():
+    from dpg_slam_b200._abi import OUTLIER_MEDIAN, OUTLIER_TRIMMED, Params
+    rng = np.random.default_rng(9)
+    for K in (1, 2, 3, 4, 10, 257, 1000):
+        d = (rng.random(K) ** 2).astype(np.float32)
+        d[: K // 3] = d[0]                                               # exact ties
+        srt = np.sort(d)
+        for ratio in (0.3, 0.5, 0.9, 1.0):
+            tau = O.outlier_threshold(d, Params.defaults(outlier_mode=OUTLIER_TRIMMED, outlier_param=ratio))
+            keep = min(max(3, int(np.floor(ratio * K))), K)
+            assert np.float32(tau) == srt[keep - 1]
+            assert (d <= np.float32(tau)).sum() >= keep                  # ties at tau are all kept
+        for factor in (0.5, 1.0, 2.5):
+            tau = O.outlier_threshold(d, Params.defaults(outlier_mode=OUTLIER_MEDIAN, outlier_param=factor))
+            lim = np.float64(srt[K // 2]) * factor
+            assert np.float64(np.float32(tau)) <= lim < np.float64(np.nextafter(np.float32(tau), np.float32(np.inf)))
+    assert O.outlier_threshold(np.ones(5, np.float32), Params.defaults()) == np.inf      # NONE: nothing is rejected
+
+
+def test_outlier_rejection_makes_icp_robust_to_a_new_object():
+    """A third of the source scan sees an object 0.3 m in front of the walls that the target scan does not contain
+    (dynamic environment): stock ICP is pulled by it, the trimmed and the median rejector are not."""
+    from dpg_slam_b200._abi import FLAG_CONVERGED, OUTLIER_MEDIAN, OUTLIER_TRIMMED, Params
+    wl, tgt, src = _room_pair()
+    moved = src.copy()
+    k0, k1 = len(src) // 3, 2 * len(src) // 3
+    laser = np.array([0.2, 0.0], np.float32)
+    v = moved[k0:k1] - laser
+    moved[k0:k1] = (v * (1.0 - 0.3 / np.linalg.norm(v, axis=1, keepdims=True)) + laser).astype(np.float32)
+    truth = wl.truth[0]
+    err = {}
+    for name, kw in (("none", {}), ("trimmed", dict(outlier_mode=OUTLIER_TRIMMED, outlier_param=0.6)),
+                     ("median", dict(outlier_mode=OUTLIER_MEDIAN, outlier_param=1.5))):
+        r = O.run_pair(moved, tgt, wl.guess[0], Params.defaults(downsample_divisor=1, cov_mode=2, **kw))
+        assert r.status & FLAG_CONVERGED
+        err[name] = float(np.hypot(r.tx - truth[0], r.ty - truth[1]))
+    assert err["none"] > 0.2 and err["trimmed"] < 0.25 * err["none"] and err["median"] < 0.25 * err["none"], err
+
+
+def test_enumerate_online_is_the_reference_loop():
+    """updatePoseGraphObsConstraints (dpg_slam.cc:255-300): successive (new, preceding), then node i < size - 2 gated
+    against — and attached to — the PRECEDING node."""
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 2, 3, 4, 5, 60, 500):
+        xy = rng.uniform(0, 12, (n, 2)).astype(np.float32)
+        ps = (np.arange(n) // 150).astype(np.int32)
+        src, tgt = O.enumerate_online(xy, ps, 5.0, 2.0)
+        want = []
+        if n >= 2:
+            new, pre = n - 1, n - 2
+            want.append((new, pre))
+            size = n - 1                                                 # dpg_nodes_.size() before the push
+            if size > 1:
+                for i in range(max(0, size - 2)):
+                    d = np.float32(np.sqrt(np.float32(np.float32((xy[i, 0] - xy[pre, 0]) ** 2) + np.float32((xy[i, 1] - xy[pre, 1]) ** 2))))
+                    if d <= (5.0 if ps[i] == ps[pre] else 2.0):
+                        want.append((pre, i))
+        assert list(zip(src.tolist(), tgt.tolist())) == want, n
