@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <mutex>
 #include <tuple>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,8 @@ struct NvtxRange {                 /* scoped NVTX range */
 };
 
 std::string g_create_error;
+std::mutex g_optin_mutex;
+std::map<std::pair<int, const void *>, size_t> g_smem_optin;   /* (device, kernel) -> dynamic shared memory opted in */
 
 struct DevBuf {
   void *p = nullptr;
@@ -73,10 +76,8 @@ struct dpgicp_ctx {
   Batch batch, scratch_batch;
   Nodes nodes;
   DevBuf stage, offsets, misc, corr, trig, enum_cnt;
-  /* per (kernel, warps, shared memory): resident CTAs per SM or clusters per device; per kernel: the dynamic shared
-   * memory opt-in already set — queried once, not on every run */
+  /* per (kernel, warps, shared memory): resident CTAs per SM or clusters per device — queried once, not on every run */
   std::map<std::tuple<const void *, int, size_t>, int> occupancy;
-  std::map<const void *, size_t> smem_optin;
   cudaEvent_t stage_ev[9] = {nullptr};
   bool stage_timing = false;
   int last_stages = 0;
@@ -182,10 +183,15 @@ int launch_icp_t(dpgicp_ctx *ctx, const KernelParams &kp, size_t smem, int64_t m
   auto kern = icp_pairs_kernel<WARPS, SEARCH, CSIZE>;
   const void *kfn = reinterpret_cast<const void *>(kern);
   /* the dynamic shared-memory opt-in and the occupancy of a shape do not change between runs: set / query once */
-  auto opt = ctx->smem_optin.find(kfn);
-  if (opt == ctx->smem_optin.end() || opt->second < smem) {
-    CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->smem_optin[kfn] = smem;
+  {
+    /* the attribute belongs to (device, function), not to a context: several contexts of one process share it, so it is
+     * tracked process-wide and only ever raised */
+    std::lock_guard<std::mutex> lock(g_optin_mutex);
+    size_t &have = g_smem_optin[std::make_pair(ctx->device, kfn)];
+    if (have < smem) {
+      CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      have = smem;
+    }
   }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3((unsigned)nw * 32, 1, 1);

@@ -460,7 +460,8 @@ __device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ clou
   const int lane = threadIdx.x & 31;
   const uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
   const f32x2 q2 = pack2(qx, qy);
-  float thr = active ? below(bd) : -1.0f;               /* -1: this lane needs nothing (any more) */
+  float thr = active ? below(bd) : -1.0f;               /* -1: this lane needs nothing (any more; or bd = 0: nothing can be closer) */
+  bool closer = false;
   float bmax = 0.0f;
   if (PRUNED) bmax = warp_max(thr);
 #ifdef DPGICP_STATS
@@ -498,10 +499,10 @@ __device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ clou
       DPG_SCAN2(0) DPG_SCAN2(1) DPG_SCAN2(2) DPG_SCAN2(3) DPG_SCAN2(4) DPG_SCAN2(5) DPG_SCAN2(6) DPG_SCAN2(7)
       DPG_SCAN2(8) DPG_SCAN2(9) DPG_SCAN2(10) DPG_SCAN2(11) DPG_SCAN2(12) DPG_SCAN2(13) DPG_SCAN2(14) DPG_SCAN2(15)
 #undef DPG_SCAN2
-      if (gd <= thr) thr = -1.0f;                       /* a strictly closer point: this lane is done */
+      if (gd <= thr) { closer = true; thr = -1.0f; }    /* a strictly closer point: this lane is done */
     }
   }
-  return active && thr < 0.0f;
+  return closer;
 }
 
 /* ------------------------------------------------------------------------------------------------
