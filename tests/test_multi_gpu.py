@@ -47,12 +47,38 @@ def _worker(rank, world, port, n_pairs, q):
             fused2 = sh.fused_records()
             sh.detach_fused_gather()
             assert fused.tobytes() == allrec.tobytes() and fused2.tobytes() == allrec.tobytes()
-            single = None
+            # root-only gather: only rank 0's buffer receives the batch (what one host-side pose-graph update needs)
+            sh.attach_fused_gather(n_pairs, root_only=True)
+            sh.run(p)
+            root = sh.fused_records()
+            sh.detach_fused_gather()
+            assert (root is None) == (rank != 0)
             if rank == 0:
+                assert root.tobytes() == allrec.tobytes()
+            # device-resident caller, sharded: every rank enumerates the list of one reoptimize() on its device and keeps
+            # its round-robin shard; records gathered into rank 0's buffer == rank 0 alone running the whole list
+            from dpg_slam_b200._abi import ENUM_REOPTIMIZE
+            ms = synth.config_multisession(n_sessions=2, scans_per_session=100, n_beams=541, seed=9, size=30.0, n_boxes=30)
+            pd = Params.defaults(cov_mode=COV_CENSI_CORR)
+            sm.upload_ranges(ms.ranges, ms.scanner)
+            sm.set_nodes(ms.poses_est, ms.passes)
+            total, local = sm.enumerate_pairs_device(ENUM_REOPTIMIZE, 5.0, 2.0, rank, world)
+            sh.n_pairs = total
+            sh.attach_fused_gather(total, root_only=True)
+            sm.run(pd)
+            enum_all = sh.fused_records(total)
+            sh.detach_fused_gather()
+            single = None
+            ok_enum = True
+            if rank == 0:
+                t1, l1 = sm.enumerate_pairs_device(ENUM_REOPTIMIZE, 5.0, 2.0, 0, 1)
+                sm.run(pd)
+                ok_enum = t1 == total and sm.fetch_results().tobytes() == enum_all.tobytes()
+                sm.upload_ranges(wl.ranges, wl.scanner)
                 sm.set_pairs(wl.src_idx, wl.tgt_idx, wl.guess)
                 sm.run(p)
                 single = sm.fetch_results()
-        ok = True if single is None else allrec.tobytes() == single.tobytes()
+        ok = ok_enum and (True if single is None else allrec.tobytes() == single.tobytes())
         q.put((rank, ok, len(allrec), int(allrec["iterations"].sum())))
     finally:
         dist.destroy_process_group()
