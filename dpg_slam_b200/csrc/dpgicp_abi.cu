@@ -316,6 +316,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
     kp.gather_world = ctx->gather_world;
     kp.gather_rank = ctx->gather_rank;
     kp.gather_fanout = ctx->gather_root_only ? 1 : ctx->gather_world;
+    kp.gather_slots = ctx->gather_n;
     for (int g = 0; g < ctx->gather_world; ++g) kp.gather_peer[g] = (dpgicp_result *)ctx->gather_peer[g];
   }
   kp.proj_window = p->projective_window;
@@ -364,6 +365,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
       if ((rc = reserve(ctx, ctx->state[k], (size_t)g0 * (size_t)kp.slot_bytes))) return rc;
       if ((rc = reserve(ctx, ctx->susp[k], (size_t)g0 * sizeof(long long)))) return rc;
     }
+    kp.slot_cap = g0;
   }
   for (int sidx = 0; sidx < n_stages; ++sidx) {
     KernelParams ks = kp;
@@ -672,6 +674,7 @@ int enumerate_into(dpgicp_ctx *ctx, Batch &b, int mode, float r_same, float r_ot
   if ((rc = reserve(ctx, b.tasks, sizeof(PairTask) * (size_t)std::max<int64_t>(local, 1)))) return rc;
   if ((rc = reserve(ctx, b.results, sizeof(dpgicp_result) * (size_t)std::max<int64_t>(local, 1)))) return rc;
   E.tasks = (PairTask *)b.tasks.p;
+  E.n_local = local;
   if (mode == DPGICP_ENUM_ONLINE) enumerate_online_kernel<true><<<blocks, 128, 0, ctx->stream>>>(E, n_chunks);
   else enumerate_reopt_kernel<true><<<blocks, 128, 0, ctx->stream>>>(E);
   ctx->launches++;

@@ -42,6 +42,26 @@
 
 #include "dpgicp.h"
 
+#include <cstdio>
+
+/* -DDPGICP_CHECK: device-side assertions on everything the kernels index with computed values (work items, suspended-
+ * state slots, neighbour seeds and matches, shared-memory capacities, gather slots, enumeration output positions) and on
+ * the agreement of the CTAs of a cluster.  A failed check prints its text and traps, so the launch — and the test that
+ * made it — fails loudly.  Compiled out of the product build; tools/build_variants.sh check=-DDPGICP_CHECK builds the
+ * checked library and the GPU suite runs against it with DPGICP_LIBRARY. */
+#ifdef DPGICP_CHECK
+#define DPG_CHECK(cond)                                                                                    \
+  do {                                                                                                     \
+    if (!(cond)) {                                                                                         \
+      printf("DPGICP_CHECK failed: %s (dpgicp_kernels.cuh:%d, block %d thread %d)\n", #cond, __LINE__,    \
+             (int)blockIdx.x, (int)threadIdx.x);                                                           \
+      __trap();                                                                                            \
+    }                                                                                                      \
+  } while (0)
+#else
+#define DPG_CHECK(cond) do { } while (0)
+#endif
+
 namespace dpg {
 
 #ifndef DPGICP_GROUP
@@ -127,6 +147,8 @@ struct KernelParams {
   int32_t gather_world, gather_rank;
   int32_t gather_fanout;              /* buffers written: gather_world (every rank's) or 1 (rank 0's only)        */
   long long pair_base;                /* dpgicp_run_range: tasks / results point at local pair pair_base of the batch */
+  long long gather_slots;             /* records every attached gather buffer can hold                               */
+  long long slot_cap;                 /* suspended-state slots available to a stage that may suspend                 */
 };
 
 /* ------------------------------------------------------------------------------------------------
@@ -587,6 +609,7 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
   /* the previous pass's neighbour seeds the bound and is the tie preference (brute force and pruned search alike) */
   bool seeded = false;
   const int seed = valid ? L.nn[i] : -1;
+  DPG_CHECK(seed >= -1 && seed < n_groups_t * kGroup);
   if (seed >= 0) {
     const float2 p = L.tgt[seed];
     const float d0 = dist2(q.x, q.y, p.x, p.y);
@@ -594,6 +617,7 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
   }
   nn_forward<PRUNED>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, seeded, st, gate);
   fwd_ok = valid && (bj != 0x7fffffff);
+  DPG_CHECK(!fwd_ok || (bj >= 0 && bj < n_groups_t * kGroup && bd <= gate));
   j_out = bj;
   d_out = bd;
   bool accept = fwd_ok;
@@ -887,6 +911,7 @@ __device__ __forceinline__ float select_tau(const SmemLayout &L, int n_pad, int 
           acc += h[u];
         }
       }
+      DPG_CHECK(__popc(__ballot_sync(0xffffffffu, mine)) == 1);
       const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
       bin = __shfl_sync(0xffffffffu, bin, src);
       before = __shfl_sync(0xffffffffu, before, src);
@@ -985,13 +1010,16 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
     if (item >= n_items) break;
     const long long pair = P.resume ? P.susp_in[item] : (P.order ? P.order[item] : (long long)item);
     const unsigned char *slot_in = P.resume ? P.state_in + (size_t)item * (size_t)P.slot_bytes : nullptr;
+    DPG_CHECK(pair >= 0 && pair < P.n_pairs);
     const PairTask task = P.tasks[pair];
+    DPG_CHECK(task.src >= 0 && task.src < P.store.n_scans && task.tgt >= 0 && task.tgt < P.store.n_scans);
     const float2 *srow = P.store.pts + (size_t)task.src * P.store.pitch;
     const float2 *trow = P.store.pts + (size_t)task.tgt * P.store.pitch;
     const int ns_full = P.store.count[task.src], nt_full = P.store.count[task.tgt];
     const int ns = (ns_full + div - 1) / div, nt = (nt_full + div - 1) / div;
     const int ts = (ns + kTile - 1) / kTile, tt = (nt + kTile - 1) / kTile;   /* tiles           */
     const int gs = ts * GPT, gt = tt * GPT;                                    /* box groups      */
+    DPG_CHECK(ns >= 0 && nt >= 0 && ts * kTile <= P.n_cap && tt * kTile <= P.n_cap);
 
     /* ---- stage both clouds in shared memory ------------------------------------------------- */
     {
@@ -1222,6 +1250,17 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       PH_MARK(3);                                     /* solve + convergence */
       __syncthreads();
       stop = L.ctl[2];
+#ifdef DPGICP_CHECK
+      if constexpr (CSIZE > 1) {                      /* every CTA of the cluster took the same decision from the same totals */
+        pair_sync<CSIZE>();
+        if (tid == 0)
+          for (int r = 0; r < CSIZE; ++r) {
+            const int32_t *c = peer_smem<CSIZE>(L.ctl, r);
+            DPG_CHECK(c[2] == L.ctl[2] && c[3] == L.ctl[3]);
+          }
+        pair_sync<CSIZE>();
+      }
+#endif
       c_corr += (tid == 0 && crank == 0) ? (unsigned long long)L.ctl[3] : 0ull;
       if (stop == 2) break;
       /* src' = step * src' in place (App. A.3-6) and refresh the source boxes */
@@ -1247,6 +1286,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
 
     if (stop == 3) {
       /* ---- suspend: current source cloud + seeds + scalars -> state slot, pair -> next queue --- */
+      DPG_CHECK(L.ctl[4] >= 0 && (long long)L.ctl[4] < P.slot_cap);
       unsigned char *slot = P.state_out + (size_t)(uint32_t)L.ctl[4] * (size_t)P.slot_bytes;
       float2 *s_src = reinterpret_cast<float2 *>(slot + kStateHeader);
       int32_t *s_nn = reinterpret_cast<int32_t *>(slot + kStateHeader + (size_t)P.n_cap * 8);
@@ -1386,6 +1426,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       if (P.gather_world > 1) {
         /* fused gather: seven 16-byte stores per peer, straight into every rank's buffer at the global slot */
         const long long slot = (long long)P.gather_rank + (P.pair_base + pair) * (long long)P.gather_world;
+        DPG_CHECK(slot >= 0 && slot < P.gather_slots);
         const int4 *src = reinterpret_cast<const int4 *>(&r);
         for (int g = 0; g < P.gather_fanout; ++g) {
           int4 *dst = reinterpret_cast<int4 *>(P.gather_peer[g] + slot);
@@ -1584,6 +1625,7 @@ struct EnumParams {
   unsigned long long *cnt;     /* count pass: pairs per node out; fill pass: start offsets in */
   PairTask *tasks;             /* fill pass: this shard's pair list                         */
   int32_t rank, world;
+  long long n_local;           /* capacity of tasks: this shard's pair count                 */
   unsigned int *amb_count;     /* pairs whose cos/sin sit too close to a binary32 rounding boundary for two */
   long long *amb_list;         /* libm implementations to be guaranteed to agree: the host re-derives these */
   int32_t amb_cap;
@@ -1681,6 +1723,7 @@ __global__ void __launch_bounds__(128) enumerate_reopt_kernel(const EnumParams E
   auto emit = [&](unsigned long long at, int src, int tgt) {
     if ((long long)(at % (unsigned long long)E.world) == (long long)E.rank) {
       const long long slot = (long long)(at / (unsigned long long)E.world);
+      DPG_CHECK(slot >= 0 && slot < E.n_local && src >= 0 && src < E.n && tgt >= 0 && tgt < E.n);
       E.tasks[slot] = make_pair_task(E, src, tgt, slot);
     }
   };
@@ -1744,6 +1787,7 @@ __global__ void __launch_bounds__(128) enumerate_online_kernel(const EnumParams 
   auto emit = [&](unsigned long long at, int src, int tgt) {
     if ((long long)(at % (unsigned long long)E.world) == (long long)E.rank) {
       const long long slot = (long long)(at / (unsigned long long)E.world);
+      DPG_CHECK(slot >= 0 && slot < E.n_local && src >= 0 && src < E.n && tgt >= 0 && tgt < E.n);
       E.tasks[slot] = make_pair_task(E, src, tgt, slot);
     }
   };
