@@ -287,6 +287,15 @@ __device__ __forceinline__ float4 lds128_off(uint32_t addr) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF) : "memory");
   return v;
 }
+/* The shared-window address of an array is "window base + offset", and left to itself the compiler re-derives the window
+ * base (S2UR SR_CgaCtaId, ULEA, ...: six dependent instructions, one of them with long latency) in front of every group
+ * scan instead of keeping the sum in a register.  An empty asm that claims to modify the value makes it opaque: it can
+ * no longer be rematerialised, only kept. */
+#ifndef DPGICP_NO_KEEP
+#define DPG_KEEP_IN_REGISTER(v) asm volatile("" : "+r"(v))
+#else
+#define DPG_KEEP_IN_REGISTER(v) do { } while (0)
+#endif
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -412,7 +421,8 @@ __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, con
                                            int n_groups, float qx, float qy, bool active, float4 qbox,
                                            float &bd, int &bj, bool seeded, SearchStats &st, float gate) {
   const int lane = threadIdx.x & 31;
-  const uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
+  uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
+  DPG_KEEP_IN_REGISTER(a_cloud); DPG_KEEP_IN_REGISTER(a_boxes);
   const f32x2 q2 = pack2(qx, qy);
   float thr = active ? (seeded ? below(bd) : bd) : -1.0f;
   float bmax = 0.0f;
@@ -480,7 +490,8 @@ __device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ clou
                                                  int n_groups, float qx, float qy, bool active, float4 qbox, float bd,
                                                  SearchStats &st) {
   const int lane = threadIdx.x & 31;
-  const uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
+  uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
+  DPG_KEEP_IN_REGISTER(a_cloud); DPG_KEEP_IN_REGISTER(a_boxes);
   const f32x2 q2 = pack2(qx, qy);
   float thr = active ? below(bd) : -1.0f;               /* -1: this lane needs nothing (any more; or bd = 0: nothing can be closer) */
   bool closer = false;
