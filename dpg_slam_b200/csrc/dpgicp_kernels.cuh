@@ -320,6 +320,8 @@ struct SmemLayout {
   float *tkey;      /* projective search only: n_cap beam-order keys of the target ...                    */
   float *skey;      /* ... and of the untransformed source                                                */
   float *ad2;       /* outlier rejection only: n_cap squared distances of the accepted pairs (+inf: none)  */
+  int lane;         /* this thread's lane, read from the special register ONCE (an S2R is long-latency; inlined helpers
+                     * that each ask for threadIdx.x again get it re-read inside the hot loops)            */
 };
 
 __host__ __device__ inline size_t smem_bytes(int n_cap, bool projective, bool trim) {
@@ -384,8 +386,7 @@ __device__ __forceinline__ void tile_boxes(float2 p, bool valid, float4 &gbox, f
 }
 
 /* store the boxes of tile `tile` of a cloud: group boxes into gb[], tile box into tb[] (may be null) */
-__device__ __forceinline__ void store_tile_boxes(float2 p, bool valid, int tile, float4 *gb, float4 *tb) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void store_tile_boxes(float2 p, bool valid, int tile, float4 *gb, float4 *tb, int lane) {
   float4 g, t;
   tile_boxes(p, valid, g, t);
   if ((lane & (kGroup - 1)) == 0) gb[tile * (kTile / kGroup) + lane / kGroup] = g;
@@ -419,8 +420,7 @@ __device__ __forceinline__ float below(float d2) {
 template <bool PRUNED>
 __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
                                            int n_groups, float qx, float qy, bool active, float4 qbox,
-                                           float &bd, int &bj, bool seeded, SearchStats &st, float gate) {
-  const int lane = threadIdx.x & 31;
+                                           float &bd, int &bj, bool seeded, SearchStats &st, float gate, int lane) {
   uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
   DPG_KEEP_IN_REGISTER(a_cloud); DPG_KEEP_IN_REGISTER(a_boxes);
   const f32x2 q2 = pack2(qx, qy);
@@ -488,8 +488,7 @@ __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, con
 template <bool PRUNED>
 __device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
                                                  int n_groups, float qx, float qy, bool active, float4 qbox, float bd,
-                                                 SearchStats &st) {
-  const int lane = threadIdx.x & 31;
+                                                 SearchStats &st, int lane) {
   uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
   DPG_KEEP_IN_REGISTER(a_cloud); DPG_KEEP_IN_REGISTER(a_boxes);
   const f32x2 q2 = pack2(qx, qy);
@@ -581,7 +580,7 @@ __device__ __forceinline__ void nn_window(const float2 *cloud, int n, int c, int
 __device__ __forceinline__ bool match_tile_projective(const SmemLayout &L, int tile, int ns, int nt, float gate,
                                                       bool reciprocal, int W, float ox, float oy, float2 &q, int &j_out,
                                                       float &d_out, bool &fwd_ok, SearchStats &st) {
-  const int lane = threadIdx.x & 31;
+  const int lane = L.lane;
   const int i = tile * kTile + lane;
   const bool valid = i < ns;
   q = L.src[i];
@@ -611,7 +610,7 @@ template <bool PRUNED>
 __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns, int n_groups_s,
                                            int n_groups_t, float gate, bool reciprocal, float2 &q,
                                            int &j_out, float &d_out, bool &fwd_ok, SearchStats &st) {
-  const int lane = threadIdx.x & 31;
+  const int lane = L.lane;
   const int i = tile * kTile + lane;
   const bool valid = i < ns;
   q = L.src[i];
@@ -626,7 +625,7 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
     const float d0 = dist2(q.x, q.y, p.x, p.y);
     if (d0 <= gate) { bd = d0; bj = seed; seeded = true; }
   }
-  nn_forward<PRUNED>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, seeded, st, gate);
+  nn_forward<PRUNED>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, seeded, st, gate, lane);
   fwd_ok = valid && (bj != 0x7fffffff);
   DPG_CHECK(!fwd_ok || (bj >= 0 && bj < n_groups_t * kGroup && bd <= gate));
   j_out = bj;
@@ -638,7 +637,7 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
     const float4 rbox = warp_box(r, fwd_ok);
     /* dist2(r, p) == dist2(p, r) bit for bit: fl(a-b) = -fl(b-a) and the square drops the sign, so source point i
      * itself is at exactly bd from r and "strictly closer than bd" is well defined */
-    const bool closer = nn_closer_exists<PRUNED>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, bd, st);
+    const bool closer = nn_closer_exists<PRUNED>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, bd, st, lane);
     accept = fwd_ok && !closer;
   }
   return accept;
@@ -982,8 +981,13 @@ __device__ __forceinline__ T *peer_smem(T *p, int rank) {
 template <int WARPS, int SEARCH, int CSIZE>
 __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(const KernelParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const SmemLayout L = carve(smem_raw, P.n_cap, SEARCH == DPGICP_SEARCH_PROJECTIVE);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  SmemLayout L = carve(smem_raw, P.n_cap, SEARCH == DPGICP_SEARCH_PROJECTIVE);
+  int tid = threadIdx.x;
+  DPG_KEEP_IN_REGISTER(tid);
+  int lane = tid & 31;
+  DPG_KEEP_IN_REGISTER(lane);
+  L.lane = lane;
+  const int warp = tid >> 5;
   const int nw = blockDim.x >> 5;            /* warps of this CTA: <= WARPS (and <= 16), chosen by the host so
                                               * that the pair's tiles divide evenly among them                 */
   const int nthreads = blockDim.x;
@@ -1062,7 +1066,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       const int k = t * kTile + lane;
       const float2 p = L.tgt[k];
       if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) L.tkey[k] = beam_key(p.x, p.y, P.sensor_x, P.sensor_y);
-      else store_tile_boxes(p, k < nt, t, L.tbox, nullptr);
+      else store_tile_boxes(p, k < nt, t, L.tbox, nullptr, lane);
     }
     for (int t = warp; t < ts; t += nw) {
       const int k = t * kTile + lane;
@@ -1077,7 +1081,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         if (k < ns) { p = xform(task.c, task.s, task.tx, task.ty, p); L.src[k] = p; }
         L.nn[k] = (P.corr_seed != nullptr && k < ns) ? P.corr_seed[k] : -1;
       }
-      if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
+      if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
     }
     if (SEARCH == DPGICP_SEARCH_PROJECTIVE && tid == 0) {
       /* accumulated transform the source in shared memory has been moved by so far */
@@ -1281,7 +1285,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           const int k = t * kTile + lane;
           float2 p = L.src[k];
           if (k < ns) { p = xform(sc, ss, stx, sty, p); L.src[k] = p; }
-          if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
+          if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
         }
       }
       if (tid == 0 && crank == 0) ++c_iters;
@@ -1343,7 +1347,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           float2 p = make_float2(kPad, kPad);
           if (k < ns) { p = xform(Tc, Ts, Ttx, Tty, __ldg(srow + (size_t)k * div)); }
           L.src[k] = p;
-          if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile);
+          if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
         }
         __syncthreads();
         for (int tile = tile0; tile < ts; tile += tile_stride) {
