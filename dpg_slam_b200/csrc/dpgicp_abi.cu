@@ -299,6 +299,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   kp.cov_mode = p->cov_mode;
   kp.cov_cap = p->cov_cap;
   kp.gate = gate_threshold(p);
+  kp.one = 1.0f;
   kp.eps = p->transformation_epsilon;
   kp.rot_thr = 1.0 - p->transformation_epsilon;
   kp.sensor_var = p->cov_sensor_variance;
@@ -323,7 +324,8 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   kp.sensor_x = p->sensor_x;
   kp.sensor_y = p->sensor_y;
   const bool trim = p->outlier_mode != DPGICP_OUTLIER_NONE;
-  const size_t smem = smem_bytes(n_cap, p->search == DPGICP_SEARCH_PROJECTIVE, trim);
+  /* shared memory of a stage: the reduction scratch grows with the CTA width */
+  auto smem_of = [&](int warps) { return smem_bytes(n_cap, p->search == DPGICP_SEARCH_PROJECTIVE, trim, warps); };
   const int search = p->search;
 
   /* stage widths (warps per pair): narrow CTAs for the bulk of the batch, wider ones for the pairs
@@ -359,7 +361,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   if (n_stages > 1) {
     /* every stage can suspend at most one pair per CTA: size the state slots for stage 0's grid */
     int g0 = -1;
-    int rc = launch_stage(ctx, search, shapes[0].warps, shapes[0].csize, kp, smem, count, &g0);
+    int rc = launch_stage(ctx, search, shapes[0].warps, shapes[0].csize, kp, smem_of(shapes[0].warps), count, &g0);
     if (rc) return rc;
     for (int k = 0; k < 2; ++k) {
       if ((rc = reserve(ctx, ctx->state[k], (size_t)g0 * (size_t)kp.slot_bytes))) return rc;
@@ -383,7 +385,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
       int next_units = -1;
       KernelParams kq = kp;
       kq.resume = 1;                        /* occupancy query for the shape the next stage will really use */
-      int rcq = launch_stage(ctx, search, shapes[sidx + 1].warps, shapes[sidx + 1].csize, kq, smem, (int64_t)1 << 40, &next_units);
+      int rcq = launch_stage(ctx, search, shapes[sidx + 1].warps, shapes[sidx + 1].csize, kq, smem_of(shapes[sidx + 1].warps), (int64_t)1 << 40, &next_units);
       if (rcq) return rcq;
       ks.handover = (long long)std::ceil((shapes[sidx + 1].csize > 1 ? ctx->handover_cluster : ctx->handover_factor) * (double)next_units);
       if (ctx->handover_factor <= 0.0) ks.handover = (long long)1 << 40;      /* development: the plain queue-dry rule */
@@ -395,7 +397,7 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
     }
     int grid = 0;
     const int64_t max_items = sidx == 0 ? count : (int64_t)grid_prev;
-    int rc = launch_stage(ctx, search, shapes[sidx].warps, shapes[sidx].csize, ks, smem, max_items, &grid);
+    int rc = launch_stage(ctx, search, shapes[sidx].warps, shapes[sidx].csize, ks, smem_of(shapes[sidx].warps), max_items, &grid);
     if (rc) return rc;
     grid_prev = grid;
     if (timing) CU_TRY(ctx, cudaEventRecord(ctx->stage_ev[sidx + 1], ctx->stream));
@@ -1573,14 +1575,14 @@ int dpgicp_fp32x2_probe(dpgicp_ctx *ctx, double *mul_add_packed) {
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {             /* rep 0 warms up */
     CU_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-    fp32x2_probe_kernel<<<blocks, threads, 0, ctx->stream>>>((float *)ctx->misc.p, iters, 1.0000001f, 1e-7f);
+    fp32x2_probe_kernel<<<blocks, threads, 0, ctx->stream>>>((float *)ctx->misc.p, iters, 1.0000001f, 1e-7f, 1.0f);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     CU_TRY(ctx, cudaEventRecord(e1, ctx->stream));
     CU_TRY(ctx, cudaEventSynchronize(e1));
     float ms = 0.f;
     CU_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
-    const double ops = (double)blocks * threads * (double)iters * 8.0 * 4.0;   /* FMUL2 + FADD2 = 4 operations */
+    const double ops = (double)blocks * threads * (double)iters * 8.0 * 4.0;   /* FMUL2 + packed sum = 2 instructions, 4 operations */
     if (rep > 0 && ms > 0.f) best = std::max(best, ops / (ms * 1e-3));
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);

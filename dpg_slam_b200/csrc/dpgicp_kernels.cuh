@@ -78,6 +78,10 @@ constexpr int   kMaxWarps = 32;
 constexpr int   kCovChunk = 16;  /* tile partials per covariance reduction round: FIXED, the summation order must not
                                   * depend on the CTA width                                                         */
 constexpr int   kStateHeader = 64;  /* bytes of scalars in front of a suspended pair's arrays      */
+/* L.nn[i] between two passes: -1 = no gated forward neighbour; otherwise the neighbour's index, with kNnRejected set
+ * when the pair failed the reciprocal test (it still seeds the next pass, but does not enter the sums) */
+constexpr int   kNnRejected = 0x40000000;
+constexpr int   kNnIndexMask = 0x3fffffff;
 
 struct PairTask {            /* 24 bytes: pair indices + the guess as matrix entries (host libm) */
   int32_t src, tgt;
@@ -113,6 +117,7 @@ struct KernelParams {
   int32_t proj_window;            /* DPGICP_SEARCH_PROJECTIVE: candidates on each side of the projected index */
   float sensor_x, sensor_y;       /* ... and the laser origin the beam order turns around                      */
   float gate;                     /* binary32 floor of max_correspondence_distance^2              */
+  float one;                      /* 1.0f, opaque to the compiler (see add2)                      */
   double eps, rot_thr, sensor_var;
   float live[3];
   /* dpgicp_correspondences hook: when corr_out != nullptr the kernel runs ONE pass for pair 0    */
@@ -188,6 +193,27 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   f32x2 r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
+}
+/* a + b per half, individually rounded.  ptxas contracts a packed mul.rn feeding a packed add.rn into ONE FFMA2 (single
+ * rounding!) whatever --fmad says — the scalar forms are left alone — and it also folds fma(a, 1.0f, b) back into that
+ * add when it can see the constant.  So the sum is issued as fma(a, one, b) with `one` = (1.0f, 1.0f) read from the
+ * kernel parameters: a * 1 is exact, the result is the correctly rounded a + b, and nothing can be fused into it. */
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b, f32x2 one) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(one), "l"(b));
+  return r;
+}
+/* ---- pair-interleaved clouds in shared memory: points 2p and 2p+1 share one 16-byte word (x0, x1, y0, y1), so that one
+ * LDS.128 of the scan loop delivers (x0, x1) and (y0, y1) as aligned register pairs and BOTH distances come out of five
+ * packed instructions (two differences, two squares, one sum: 2.5 issue slots per distance instead of 3).  HBM rows and
+ * TMA-staged rows are plain (x, y) pairs; the staging loops re-arrange each 32-point tile in place. ---- */
+__device__ __forceinline__ float2 ld_pt(const float2 *cloud, int k) {
+  const float *f = reinterpret_cast<const float *>(cloud) + ((k >> 1) << 2) + (k & 1);
+  return make_float2(f[0], f[2]);
+}
+__device__ __forceinline__ void st_pt(float2 *cloud, int k, float2 p) {
+  float *f = reinterpret_cast<float *>(cloud) + ((k >> 1) << 2) + (k & 1);
+  f[0] = p.x; f[2] = p.y;
 }
 /* dist2(q, p) with q = (qx, qy), p = (px, py) packed: (qx - px)^2 + (qy - py)^2, same roundings as dist2() */
 __device__ __forceinline__ float dist2_packed(f32x2 q, f32x2 p) {
@@ -312,7 +338,8 @@ struct SmemLayout {
   float4 *stile;    /* n_cap/32 boxes of the source tiles (query boxes of the forward search)        */
   int32_t *tcnt;    /* n_cap/32 accepted per source tile (rank for the covariance cap)              */
   long long *red;   /* 48 int64: [0..15] totals of the pass, [16..47] this CTA's totals by pass parity (clusters) */
-  double *dpart;    /* kMaxWarps * 12 partial double sums (deterministic order)                     */
+  double *dpart;    /* dpart_bytes(warps): per-warp int64 partials of the pass (two parities) / 16 tile partials of
+                     * the covariance (deterministic order) / the rejector's histogram                            */
   float *step;      /* 4 */
   int32_t *ctl;     /* [0] item lo [1] item hi [2] stop [3] K [4] slot                               */
   uint64_t *mbar;
@@ -324,13 +351,21 @@ struct SmemLayout {
                      * that each ask for threadIdx.x again get it re-read inside the hot loops)            */
 };
 
-__host__ __device__ inline size_t smem_bytes(int n_cap, bool projective, bool trim) {
+/* scratch for the reductions, sized by the CTA width: 2 parities x warps x 12 int64 partials of a pass, and at least
+ * kCovChunk x 12 doubles for the covariance (1536 bytes, which also holds the rejector's 256-bin histogram).  Narrow
+ * CTAs are the ones that share an SM eight at a time, so every kilobyte counts there. */
+__host__ __device__ inline size_t dpart_bytes(int warps) {
+  const size_t pass = (size_t)2 * warps * 12 * 8, cov = (size_t)kCovChunk * 12 * 8;
+  return pass > cov ? pass : cov;
+}
+
+__host__ __device__ inline size_t smem_bytes(int n_cap, bool projective, bool trim, int warps) {
   const int g = n_cap / kGroup, t = n_cap / kTile;
-  return (size_t)n_cap * (8 + 8 + 4) + (size_t)g * (16 + 16) + (size_t)t * (16 + 4) + 48 * 8 + kMaxWarps * 12 * 8 + 16 + 32 +
+  return (size_t)n_cap * (8 + 8 + 4) + (size_t)g * (16 + 16) + (size_t)t * (16 + 4) + 48 * 8 + dpart_bytes(warps) + 16 + 32 +
          16 + 64 + 16 + (projective ? (size_t)n_cap * 8 : 0) + (trim ? (size_t)n_cap * 4 : 0);
 }
 
-__device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap, bool projective) {
+__device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap, bool projective, int warps) {
   const int g = n_cap / kGroup, t = n_cap / kTile;
   SmemLayout L;
   size_t o = 0;
@@ -341,7 +376,7 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap, bool
   L.sbox = (float4 *)(base + o); o += (size_t)g * 16;
   L.stile = (float4 *)(base + o); o += (size_t)t * 16;
   L.red = (long long *)(base + o); o += 48 * 8;
-  L.dpart = (double *)(base + o);  o += kMaxWarps * 12 * 8;
+  L.dpart = (double *)(base + o);  o += dpart_bytes(warps);
   L.mbar = (uint64_t *)(base + o); o += 16;
   L.tcnt = (int32_t *)(base + o); o += (size_t)t * 4;
   L.step = (float *)(base + o);   o += 16;
@@ -420,10 +455,12 @@ __device__ __forceinline__ float below(float d2) {
 template <bool PRUNED>
 __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
                                            int n_groups, float qx, float qy, bool active, float4 qbox,
-                                           float &bd, int &bj, bool seeded, SearchStats &st, float gate, int lane) {
+                                           float &bd, int &bj, bool seeded, SearchStats &st, float gate, int lane,
+                                           float one) {
+  const f32x2 one2 = pack2(one, one);
   uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
   DPG_KEEP_IN_REGISTER(a_cloud); DPG_KEEP_IN_REGISTER(a_boxes);
-  const f32x2 q2 = pack2(qx, qy);
+  const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy);
   float thr = active ? (seeded ? below(bd) : bd) : -1.0f;
   float bmax = 0.0f;
   if (PRUNED) bmax = warp_max(thr);
@@ -456,9 +493,9 @@ __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, con
       float gd = __int_as_float(0x7f800000);
 #define DPG_SCAN2(T)                                                                                  \
       if (2 * (T) < kGroup) {                                                                         \
-        const float4 p = lds128_off<16 * (T)>(a_grp);     /* two points per LDS.128, broadcast */     \
-        dd[(2 * (T)) % kGroup] = dist2_packed(q2, pack2(p.x, p.y));                                   \
-        dd[(2 * (T) + 1) % kGroup] = dist2_packed(q2, pack2(p.z, p.w));                               \
+        const float4 p = lds128_off<16 * (T)>(a_grp);     /* (x0, x1, y0, y1) of two points, broadcast */ \
+        const f32x2 ex = sub2(qx2, pack2(p.x, p.y)), ey = sub2(qy2, pack2(p.z, p.w));                  \
+        unpack2(add2(mul2(ex, ex), mul2(ey, ey), one2), dd[(2 * (T)) % kGroup], dd[(2 * (T) + 1) % kGroup]); \
         gd = fminf(fminf(gd, dd[(2 * (T)) % kGroup]), dd[(2 * (T) + 1) % kGroup]);                     \
       }
       DPG_SCAN2(0) DPG_SCAN2(1) DPG_SCAN2(2) DPG_SCAN2(3) DPG_SCAN2(4) DPG_SCAN2(5) DPG_SCAN2(6) DPG_SCAN2(7)
@@ -488,10 +525,11 @@ __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, con
 template <bool PRUNED>
 __device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
                                                  int n_groups, float qx, float qy, bool active, float4 qbox, float bd,
-                                                 SearchStats &st, int lane) {
+                                                 SearchStats &st, int lane, float one) {
+  const f32x2 one2 = pack2(one, one);
   uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
   DPG_KEEP_IN_REGISTER(a_cloud); DPG_KEEP_IN_REGISTER(a_boxes);
-  const f32x2 q2 = pack2(qx, qy);
+  const f32x2 q2 = pack2(qx, qy), qx2 = pack2(qx, qx), qy2 = pack2(qy, qy);
   float thr = active ? below(bd) : -1.0f;               /* -1: this lane needs nothing (any more; or bd = 0: nothing can be closer) */
   bool closer = false;
   float bmax = 0.0f;
@@ -526,7 +564,10 @@ __device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ clou
 #define DPG_SCAN2(T)                                                                                  \
       if (2 * (T) < kGroup) {                                                                         \
         const float4 p = lds128_off<16 * (T)>(a_grp);                                                 \
-        gd = fminf(fminf(gd, dist2_packed(q2, pack2(p.x, p.y))), dist2_packed(q2, pack2(p.z, p.w)));  \
+        const f32x2 ex = sub2(qx2, pack2(p.x, p.y)), ey = sub2(qy2, pack2(p.z, p.w));                  \
+        float d0, d1;                                                                                 \
+        unpack2(add2(mul2(ex, ex), mul2(ey, ey), one2), d0, d1);                                      \
+        gd = fminf(fminf(gd, d0), d1);                                                                \
       }
       DPG_SCAN2(0) DPG_SCAN2(1) DPG_SCAN2(2) DPG_SCAN2(3) DPG_SCAN2(4) DPG_SCAN2(5) DPG_SCAN2(6) DPG_SCAN2(7)
       DPG_SCAN2(8) DPG_SCAN2(9) DPG_SCAN2(10) DPG_SCAN2(11) DPG_SCAN2(12) DPG_SCAN2(13) DPG_SCAN2(14) DPG_SCAN2(15)
@@ -569,7 +610,7 @@ __device__ __forceinline__ void nn_window(const float2 *cloud, int n, int c, int
   bd = __int_as_float(0x7f800000);
   bj = -1;
   for (int j = j0; j < j1; ++j) {
-    const float2 p = cloud[j];
+    const float2 p = ld_pt(cloud, j);
     const float d = dist2_packed(q2, pack2(p.x, p.y));
     if (d < bd) { bd = d; bj = j; }
   }
@@ -583,7 +624,7 @@ __device__ __forceinline__ bool match_tile_projective(const SmemLayout &L, int t
   const int lane = L.lane;
   const int i = tile * kTile + lane;
   const bool valid = i < ns;
-  q = L.src[i];
+  q = ld_pt(L.src, i);
   float bd = __int_as_float(0x7f800000);
   int bj = -1;
   if (valid) nn_window(L.tgt, nt, key_lower_bound(L.tkey, nt, beam_key(q.x, q.y, ox, oy)), W, q.x, q.y, bd, bj, st);
@@ -593,7 +634,7 @@ __device__ __forceinline__ bool match_tile_projective(const SmemLayout &L, int t
   bool accept = fwd_ok;
   if (reciprocal && fwd_ok) {
     /* the matched target point in the source scan's own frame: R^T (r - t) */
-    const float2 r = L.tgt[bj];
+    const float2 r = ld_pt(L.tgt, bj);
     const float fc = L.fin[0], fs = L.fin[1];
     const float ex = __fsub_rn(r.x, L.fin[2]), ey = __fsub_rn(r.y, L.fin[3]);
     const float bx = __fadd_rn(__fmul_rn(fc, ex), __fmul_rn(fs, ey));
@@ -608,24 +649,25 @@ __device__ __forceinline__ bool match_tile_projective(const SmemLayout &L, int t
 
 template <bool PRUNED>
 __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns, int n_groups_s,
-                                           int n_groups_t, float gate, bool reciprocal, float2 &q,
+                                           int n_groups_t, float gate, bool reciprocal, float one, float2 &q,
                                            int &j_out, float &d_out, bool &fwd_ok, SearchStats &st) {
   const int lane = L.lane;
   const int i = tile * kTile + lane;
   const bool valid = i < ns;
-  q = L.src[i];
+  q = ld_pt(L.src, i);
   float bd = gate;
   int bj = 0x7fffffff;
   /* the previous pass's neighbour seeds the bound and is the tie preference (brute force and pruned search alike) */
   bool seeded = false;
-  const int seed = valid ? L.nn[i] : -1;
+  int seed = valid ? L.nn[i] : -1;
+  if (seed >= 0) seed &= kNnIndexMask;
   DPG_CHECK(seed >= -1 && seed < n_groups_t * kGroup);
   if (seed >= 0) {
-    const float2 p = L.tgt[seed];
+    const float2 p = ld_pt(L.tgt, seed);
     const float d0 = dist2(q.x, q.y, p.x, p.y);
     if (d0 <= gate) { bd = d0; bj = seed; seeded = true; }
   }
-  nn_forward<PRUNED>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, seeded, st, gate, lane);
+  nn_forward<PRUNED>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, seeded, st, gate, lane, one);
   fwd_ok = valid && (bj != 0x7fffffff);
   DPG_CHECK(!fwd_ok || (bj >= 0 && bj < n_groups_t * kGroup && bd <= gate));
   j_out = bj;
@@ -633,11 +675,11 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
   bool accept = fwd_ok;
   if (reciprocal && __any_sync(0xffffffffu, fwd_ok)) {
     float2 r = make_float2(0.f, 0.f);
-    if (fwd_ok) r = L.tgt[bj];
+    if (fwd_ok) r = ld_pt(L.tgt, bj);
     const float4 rbox = warp_box(r, fwd_ok);
     /* dist2(r, p) == dist2(p, r) bit for bit: fl(a-b) = -fl(b-a) and the square drops the sign, so source point i
      * itself is at exactly bd from r and "strictly closer than bd" is well defined */
-    const bool closer = nn_closer_exists<PRUNED>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, bd, st, lane);
+    const bool closer = nn_closer_exists<PRUNED>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, bd, st, lane, one);
     accept = fwd_ok && !closer;
   }
   return accept;
@@ -652,7 +694,7 @@ __device__ __forceinline__ bool match_any(const SmemLayout &L, const KP &P, int 
     return match_tile_projective(L, tile, ns, nt, P.gate, P.use_reciprocal != 0, P.proj_window, P.sensor_x, P.sensor_y, q, j,
                                  d, fwd, st);
   else
-    return match_tile<SEARCH == DPGICP_SEARCH_PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, q, j, d, fwd, st);
+    return match_tile<SEARCH == DPGICP_SEARCH_PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, P.one, q, j, d, fwd, st);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -803,23 +845,23 @@ __device__ __forceinline__ long long fxp(double v) { return __double2ll_rn(__dmu
 template <typename KP>
 __device__ __forceinline__ void accumulate_pair(const SmemLayout &L, const KP &P, float2 q, int j, float d, int nt,
                                                 long long (&m)[10], int &m_k) {
-  const float2 t = L.tgt[j];
+  const float2 t = ld_pt(L.tgt, j);
   const double px = q.x, py = q.y, qx = t.x, qy = t.y;
   if (P.metric == DPGICP_METRIC_POINT_TO_LINE) {
     /* line through the matched target point and its closer beam neighbour (oracle:
      * accumulate_normal_eq); m0..m5 = A (11,12,13,22,23,33), m6..m8 = sum J^T r */
     int j2 = -1;
     float best = __int_as_float(0x7f800000);
-    if (j - 1 >= 0) { const float2 a = L.tgt[j - 1]; best = dist2(q.x, q.y, a.x, a.y); j2 = j - 1; }
+    if (j - 1 >= 0) { const float2 a = ld_pt(L.tgt, j - 1); best = dist2(q.x, q.y, a.x, a.y); j2 = j - 1; }
     if (j + 1 < nt) {
-      const float2 a = L.tgt[j + 1];
+      const float2 a = ld_pt(L.tgt, j + 1);
       const float dn = dist2(q.x, q.y, a.x, a.y);
       if (dn < best) { best = dn; j2 = j + 1; }
     }
     bool line = false;
     double nx = 0.0, ny = 0.0;
     if (j2 >= 0) {
-      const float2 a = L.tgt[j2];
+      const float2 a = ld_pt(L.tgt, j2);
       const float seg = dist2(a.x, a.y, t.x, t.y);
       if (seg > 0.0f && seg <= P.gate) {
         const double tx = __dsub_rn((double)a.x, qx), ty = __dsub_rn((double)a.y, qy);
@@ -956,8 +998,15 @@ __device__ __forceinline__ float select_tau(const SmemLayout &L, int n_pad, int 
 #ifndef DPGICP_TARGET_WARPS
 #define DPGICP_TARGET_WARPS 28
 #endif
+/* CTAs of up to 4 warps.  32 (8 x 4 warps per SM, 64 registers, fits since the reduction scratch is sized by the CTA
+ * width) was measured equal to 28 (7 x 4 warps, 72 registers) within 0.5 %: the stage is held back by issue slots,
+ * shared-memory write-back and the FP32 pipe together, not by latency that more resident warps could hide. */
+#ifndef DPGICP_TARGET_WARPS_NARROW
+#define DPGICP_TARGET_WARPS_NARROW 28
+#endif
 __host__ __device__ constexpr int min_ctas(int warps) {
-  return (DPGICP_TARGET_WARPS / warps) < 1 ? 1 : (DPGICP_TARGET_WARPS / warps) > 16 ? 16 : (DPGICP_TARGET_WARPS / warps);   /* 16, 17, 32 -> 1 */
+  const int target = warps <= 4 ? DPGICP_TARGET_WARPS_NARROW : DPGICP_TARGET_WARPS;
+  return (target / warps) < 1 ? 1 : (target / warps) > 16 ? 16 : (target / warps);   /* 16, 17, 32 -> 1 */
 }
 
 /* CSIZE > 1: a thread-block CLUSTER of CSIZE CTAs (one per SM) works on one pair — used by the host for the
@@ -981,7 +1030,7 @@ __device__ __forceinline__ T *peer_smem(T *p, int rank) {
 template <int WARPS, int SEARCH, int CSIZE>
 __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(const KernelParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemLayout L = carve(smem_raw, P.n_cap, SEARCH == DPGICP_SEARCH_PROJECTIVE);
+  SmemLayout L = carve(smem_raw, P.n_cap, SEARCH == DPGICP_SEARCH_PROJECTIVE, (int)(blockDim.x >> 5));
   int tid = threadIdx.x;
   DPG_KEEP_IN_REGISTER(tid);
   int lane = tid & 31;
@@ -1058,19 +1107,22 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       mbar_phase ^= 1u;
     }
     __syncthreads();
-    /* pad to whole tiles, apply the guess (PCL transformCloud(input, guess), App. A.2), boxes */
-    for (int k = nt + tid; k < tt * kTile; k += nthreads) L.tgt[k] = make_float2(kPad, kPad);
-    for (int k = ns + tid; k < ts * kTile; k += nthreads) L.src[k] = make_float2(kPad, kPad);
-    __syncthreads();
+    /* every warp re-arranges its tiles in place from the staged (x, y) rows to pair-interleaved words (all 32 lanes
+     * read their point before any lane writes), pads to whole tiles, applies the guess to the source (PCL
+     * transformCloud(input, guess), App. A.2) and forms the boxes.  A resumed source already is pair-interleaved. */
     for (int t = warp; t < tt; t += nw) {
       const int k = t * kTile + lane;
-      const float2 p = L.tgt[k];
+      const float2 p = k < nt ? L.tgt[k] : make_float2(kPad, kPad);
+      __syncwarp();
+      st_pt(L.tgt, k, p);
       if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) L.tkey[k] = beam_key(p.x, p.y, P.sensor_x, P.sensor_y);
       else store_tile_boxes(p, k < nt, t, L.tbox, nullptr, lane);
     }
     for (int t = warp; t < ts; t += nw) {
       const int k = t * kTile + lane;
-      float2 p = L.src[k];
+      float2 p = make_float2(kPad, kPad);
+      if (k < ns) p = P.resume ? ld_pt(L.src, k) : L.src[k];
+      __syncwarp();
       if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) {
         /* keys of the UNTRANSFORMED source (a resumed pair holds the current one: take the original from the store) */
         float2 o = p;
@@ -1078,9 +1130,10 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         L.skey[k] = beam_key(o.x, o.y, P.sensor_x, P.sensor_y);
       }
       if (!P.resume) {
-        if (k < ns) { p = xform(task.c, task.s, task.tx, task.ty, p); L.src[k] = p; }
+        if (k < ns) p = xform(task.c, task.s, task.tx, task.ty, p);
         L.nn[k] = (P.corr_seed != nullptr && k < ns) ? P.corr_seed[k] : -1;
       }
+      if (!P.resume || k >= ns) st_pt(L.src, k, p);
       if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
     }
     if (SEARCH == DPGICP_SEARCH_PROJECTIVE && tid == 0) {
@@ -1139,24 +1192,32 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
 #define PH_MARK(k) do { } while (0)
 #endif
     for (;;) {
-      long long m[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-      int m_k = 0;
+      /* phase 1: the searches.  Their result goes to L.nn (neighbour + rejected bit), so that the twenty registers of
+       * moment accumulators are not live across the search loops */
       for (int tile = tile0; tile < ts; tile += tile_stride) {
         float2 q; int j; float d; bool fwd;
         const bool acc = match_any<SEARCH>(L, P, tile, ns, nt, gs, gt, q, j, d, fwd, stats);
         const int i = tile * kTile + lane;
-        if (i < ns) L.nn[i] = fwd ? j : -1;           /* seed (and tie preference) of the next pass */
+        if (i < ns) L.nn[i] = fwd ? (acc ? j : (j | kNnRejected)) : -1;   /* seed (and tie preference) of the next pass */
         if (trim) L.ad2[i] = acc ? d : __int_as_float(0x7f800000);
-        else if (acc) accumulate_pair(L, P, q, j, d, nt, m, m_k);
       }
+      /* outlier rejection: threshold from the accepted distances of the whole pair */
+      float tau = __int_as_float(0x7f800000);
       if (trim) {
-        /* outlier rejection: threshold from the accepted distances of the whole pair, then the sums over the kept */
         __syncthreads();
-        const float tau = select_tau(L, ts * kTile, P.outlier_mode, P.outlier_param);
-        for (int tile = tile0; tile < ts; tile += tile_stride) {
-          const int i = tile * kTile + lane;
-          const float d = L.ad2[i];
-          if (d < __int_as_float(0x7f800000) && d <= tau) accumulate_pair(L, P, L.src[i], L.nn[i], d, nt, m, m_k);
+        tau = select_tau(L, ts * kTile, P.outlier_mode, P.outlier_param);
+      }
+      /* phase 2: the sums over the accepted (and kept) pairs of this warp's tiles */
+      long long m[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      int m_k = 0;
+      for (int tile = tile0; tile < ts; tile += tile_stride) {
+        const int i = tile * kTile + lane;
+        const int v = (i < ns) ? L.nn[i] : -1;
+        if (v >= 0 && !(v & kNnRejected)) {
+          const float2 q = ld_pt(L.src, i);
+          const float2 t = ld_pt(L.tgt, v);
+          const float d = dist2(q.x, q.y, t.x, t.y);          /* the search's own value: same operands, same roundings */
+          if (!trim || d <= tau) accumulate_pair(L, P, q, v, d, nt, m, m_k);
         }
       }
       PH_MARK(0);                                     /* own tiles */
@@ -1167,7 +1228,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       if (lane == 0) {
         /* per-warp partials in shared memory (plain stores; a 64-bit shared atomicAdd is a CAS spin loop);
          * the slots alias L.dpart, which is only used by the covariance after the pass loop */
-        long long *w = reinterpret_cast<long long *>(L.dpart) + (parity * 16 + warp) * 12;
+        long long *w = reinterpret_cast<long long *>(L.dpart) + (parity * nw + warp) * 12;
 #pragma unroll
         for (int k = 0; k < 10; ++k) w[k] = m[k];
         w[10] = (long long)m_k;
@@ -1180,7 +1241,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         /* cluster: each CTA first folds its own warps into one set of 11 totals, so that a peer reads
          * 11 values per CTA through distributed shared memory (latency ~200 cycles each), not 11 per warp */
         if (warp == 0 && lane < 11) {
-          const long long *w = reinterpret_cast<const long long *>(L.dpart) + parity * 16 * 12 + lane;
+          const long long *w = reinterpret_cast<const long long *>(L.dpart) + parity * nw * 12 + lane;
           long long tot = 0;
           for (int q = 0; q < nw; ++q) tot += w[q * 12];
           L.red[16 + parity * 16 + lane] = tot;
@@ -1201,7 +1262,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       } else if (warp == 0) {
         /* exact integer totals: lane k adds value k over the warps (any order gives the same bits) */
         if (lane < 11) {
-          const long long *w = reinterpret_cast<const long long *>(L.dpart) + parity * 16 * 12 + lane;
+          const long long *w = reinterpret_cast<const long long *>(L.dpart) + parity * nw * 12 + lane;
           long long tot = 0;
           for (int q = 0; q < nw; ++q) tot += w[q * 12];
           L.red[lane] = tot;
@@ -1283,8 +1344,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         const float sc = L.step[0], ss = L.step[1], stx = L.step[2], sty = L.step[3];
         for (int t = warp; t < ts; t += nw) {
           const int k = t * kTile + lane;
-          float2 p = L.src[k];
-          if (k < ns) { p = xform(sc, ss, stx, sty, p); L.src[k] = p; }
+          float2 p = ld_pt(L.src, k);
+          if (k < ns) { p = xform(sc, ss, stx, sty, p); st_pt(L.src, k, p); }
           if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
         }
       }
@@ -1305,7 +1366,9 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       unsigned char *slot = P.state_out + (size_t)(uint32_t)L.ctl[4] * (size_t)P.slot_bytes;
       float2 *s_src = reinterpret_cast<float2 *>(slot + kStateHeader);
       int32_t *s_nn = reinterpret_cast<int32_t *>(slot + kStateHeader + (size_t)P.n_cap * 8);
-      for (int k = tid; k < ns; k += nthreads) { s_src[k] = L.src[k]; s_nn[k] = L.nn[k]; }
+      /* the cloud goes out as it lies in shared memory (pair-interleaved words): whole pairs, so ns rounded up to even */
+      for (int k = tid; k < ((ns + 1) & ~1); k += nthreads) s_src[k] = L.src[k];
+      for (int k = tid; k < ns; k += nthreads) s_nn[k] = L.nn[k];
       if (tid == 0) {
         SuspHeader h;
         h.fc = fc; h.fs = fs; h.ftx = ftx; h.fty = fty; h.mse = mse; h.mse_prev = mse_prev;
@@ -1346,7 +1409,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           const int k = t * kTile + lane;
           float2 p = make_float2(kPad, kPad);
           if (k < ns) { p = xform(Tc, Ts, Ttx, Tty, __ldg(srow + (size_t)k * div)); }
-          L.src[k] = p;
+          st_pt(L.src, k, p);
           if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
         }
         __syncthreads();
@@ -1399,7 +1462,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
             const int rank = prefix + __popc(bal & ((1u << lane) - 1u));
             if (j >= 0) {
               const float2 p = __ldg(srow + (size_t)i * div);
-              const float2 q = L.tgt[j];
+              const float2 q = ld_pt(L.tgt, j);
               const bool in_d = (P.cov_cap <= 0) || (rank < P.cov_cap);
               cov_terms(p.x, p.y, q.x, q.y, ca, sa, x, y, true, in_d, acc);
             }
@@ -1938,19 +2001,18 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float *out, int iters, 
   if (s == 123.456f) out[0] = s;       /* keeps the chains alive; practically never true */
 }
 
-/* the same chains with packed pairs: FMUL2 + FADD2 (two individually rounded results per instruction) */
-__global__ void __launch_bounds__(256) fp32x2_probe_kernel(float *out, int iters, float a, float b) {
+/* the same chains with packed pairs, two individually rounded results per instruction: FMUL2 then the packed sum in
+ * the form the distance loop issues it (add2: an FFMA2 by an opaque 1.0f, because ptxas would contract a packed
+ * mul.rn + add.rn pair into ONE fused FFMA2 — which is what this probe measured, unnoticed, until round 2: half the
+ * instructions it was credited with) */
+__global__ void __launch_bounds__(256) fp32x2_probe_kernel(float *out, int iters, float a, float b, float one) {
   f32x2 x[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) x[k] = pack2((float)(threadIdx.x + k) * 1e-3f, (float)(threadIdx.x + k) * 2e-3f);
-  const f32x2 a2 = pack2(a, a), b2 = pack2(b, b);
+  const f32x2 a2 = pack2(a, a), b2 = pack2(b, b), one2 = pack2(one, one);
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      f32x2 r;
-      asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(mul2(x[k], a2)), "l"(b2));
-      x[k] = r;
-    }
+    for (int k = 0; k < 8; ++k) x[k] = add2(mul2(x[k], a2), b2, one2);
   }
   float s = 0.f;
 #pragma unroll
