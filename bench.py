@@ -261,10 +261,34 @@ def load_peaks():
         return {}
 
 
+def fp32_peak(probe, nominal):
+    """Rate of separately rounded binary32 multiplies and adds on this GPU, measured in this run: the scalar FMUL+FADD
+    chains and the packed FMUL2 + packed-sum chains give the same ~37 T op/s (a packed instruction carries two results but
+    takes two pipe cycles; it saves issue slots, not FP32 time).  Until round 2 the packed probe reported twice that:
+    ptxas had contracted its mul.rn.f32x2 / add.rn.f32x2 pairs into single fused FFMA2 instructions."""
+    measured = probe["mul_add_ops_per_s"] / 1e12
+    packed = probe.get("mul_add_packed_ops_per_s", 0.0) / 1e12
+    peak = max(measured, packed)
+    return (peak if peak > 0 else nominal), measured, packed
+
+
+def smem_block(counters, k_ms, sm_mhz, n_sm=148):
+    """The other ceiling of the scan loop: every distance evaluation needs the searched point in the lane's registers —
+    8 bytes per lane, 256 bytes per warp and point — and the shared-memory pipe writes back 128 bytes per cycle and SM
+    (an LDS.128 occupies it for 4 cycles whether or not the address is a broadcast; ncu: lsu_writeback_active, profiles/).
+    cycles = 2 per warp-level point evaluation."""
+    warp_points = counters["distance_evals"] / 32.0
+    cycles = 2.0 * warp_points
+    avail = k_ms * 1e-3 * sm_mhz * 1e6 * n_sm
+    return {"bound": "shared-memory write-back (LDS.128 broadcast of the searched points)", "cycles_per_warp_point": 2.0,
+            "busy_cycles_per_launch": cycles, "available_cycles": avail, "frac": cycles / avail,
+            "note": "distance loop only; box tests, seeds and moments add a few percent (ncu l1tex__lsu_writeback_active)"}
+
+
 def roofline_block(name, search, k_ms, stage_ms, counters, rec_local, ns, nt, probe, peaks):
     """FP32 roofline of icp_pairs_kernel for rank 0's launch.  `achieved` is the EXECUTED FP32 work (the distance
     arithmetic the kernel really issued, counted on the device) over the live kernel time, against the measured rate of
-    the instruction mix the bit-exact loop may use (packed, separately rounded FMUL2 + FADD2): a fraction <= 1.  The
+    the instruction mix the bit-exact loop may use (separately rounded multiplies and adds, no FMA): a fraction <= 1.  The
     exact pruned search skips most of the brute-force evaluations SURVEY 8d's normative formula counts; that ratio is
     reported as algorithmic_speedup, not folded into the fraction."""
     icp_fl, cov_fl = algorithmic_flops(rec_local, ns, nt, counters["correspondences"])
@@ -273,12 +297,10 @@ def roofline_block(name, search, k_ms, stage_ms, counters, rec_local, ns, nt, pr
     exec_tflops = exec_flops / (k_ms * 1e-3) / 1e12
     sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
     nominal = 148 * 128 * sm_mhz * 1e6 / 1e12
-    measured = probe["mul_add_ops_per_s"] / 1e12
-    packed = probe.get("mul_add_packed_ops_per_s", 0.0) / 1e12
-    peak = packed if packed > 0 else (measured if measured > 0 else nominal)
+    peak, measured, packed = fp32_peak(probe, nominal)
     alg_bytes = float(np.sum(8.0 * (ns + nt) + 20 + 112))
     traffic, traffic_source, ncu_inst = None, None, None
-    prof_name = {"corridor": "r02_icp_kernel_ncu.json"}.get(name)
+    prof_name = {"corridor": "r02_final_icp_kernel_ncu.json"}.get(name)
     if prof_name and search == "pruned":
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
@@ -292,9 +314,10 @@ def roofline_block(name, search, k_ms, stage_ms, counters, rec_local, ns, nt, pr
            "bound": "fp32", "achieved": exec_tflops, "peak": peak, "unit": "TFLOP/s", "frac": exec_tflops / peak,
            "achieved_definition": "EXECUTED FP32 work: (5 flop x distance evaluations + 9 flop x box lower bounds) counted on the device "
                                   "/ live kernel time (CUDA events on the launching stream)",
-           "peak_source": "measured on this GPU in this run by dpgicp_fp32x2_probe: separately rounded FMUL2+FADD2 chains (packed pairs, "
-                          "2 operations per issue slot; the bit-exact distance loop may not use FMA); MEASURED_PEAKS.json has no FP32 "
-                          f"figure; nominal scalar rate 148 SM x 128 lanes x {sm_mhz} MHz = {nominal:.1f}",
+           "peak_source": "measured on this GPU in this run (dpgicp_fp32_probe / dpgicp_fp32x2_probe): separately rounded multiply+add "
+                          "chains, scalar and packed alike (the bit-exact distance loop may not use FMA; a packed instruction carries two "
+                          "results but takes two pipe cycles); MEASURED_PEAKS.json has no FP32 figure; nominal rate 148 SM x 128 lanes x "
+                          f"{sm_mhz} MHz = {nominal:.1f}",
            "algorithmic_tflops": alg_tflops, "algorithmic_speedup": (icp_fl + cov_fl) / max(exec_flops, 1.0),
            "algorithmic_definition": "SURVEY 8d brute-force flops I*(5*Ns*Nt+8*Ns)+14*K + 60*N_H+45*min(K,200) per kernel time; the exact "
                                      "pruned search executes 1/algorithmic_speedup of them",
@@ -302,7 +325,8 @@ def roofline_block(name, search, k_ms, stage_ms, counters, rec_local, ns, nt, pr
            "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                    "peak_gbs": peaks.get("hbm_gbs"),
                    "frac": (alg_bytes / (k_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None},
-           "fp32_probe_tops": {"mul_add": measured, "mul_add_packed": packed, "fma": probe["fma_ops_per_s"] / 1e12}}
+           "fp32_probe_tops": {"mul_add": measured, "mul_add_packed": packed, "fma": probe["fma_ops_per_s"] / 1e12},
+           "smem": smem_block(counters, k_ms, sm_mhz)}
     if ncu_inst:
         issue_peak = 4.0 * 148 * sm_mhz * 1e6
         out["issue_frac"] = ncu_inst / (k_ms * 1e-3) / issue_peak
@@ -853,15 +877,16 @@ def run_product_multisession(args):
         if rank == 0:
             probe = sm.fp32_probe()
             sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
-            packed = probe.get("mul_add_packed_ops_per_s", 0.0) / 1e12
+            peak32, _, _ = fp32_peak(probe, 148 * 128 * sm_mhz * 1e6 / 1e12)
             k_ms = dev_ms / args.steps
             exec_tflops = (5.0 * counters["distance_evals"] + 9.0 * counters["box_tests"]) / (k_ms * 1e-3) / 1e12
             roof = {"kernel": "dpg::icp_pairs_kernel<WARPS,SEARCH,CLUSTER> (stage chain, rank 0's shard)", "bound": "fp32",
-                    "achieved": exec_tflops, "peak": packed, "unit": "TFLOP/s", "frac": exec_tflops / packed if packed else None,
+                    "achieved": exec_tflops, "peak": peak32, "unit": "TFLOP/s", "frac": exec_tflops / peak32 if peak32 else None,
                     "achieved_definition": "EXECUTED FP32 work: (5 flop x distance evaluations + 9 flop x box lower bounds) counted on the device / "
                                            "live kernel time (CUDA events on the launching stream)",
-                    "peak_source": "dpgicp_fp32x2_probe in this run (packed FMUL2+FADD2); nominal scalar "
-                                   f"{148 * 128 * sm_mhz * 1e6 / 1e12:.1f}",
+                    "peak_source": "dpgicp_fp32_probe / dpgicp_fp32x2_probe in this run (separately rounded multiply+add chains, "
+                                   f"scalar and packed alike); nominal {148 * 128 * sm_mhz * 1e6 / 1e12:.1f}",
+                    "smem": smem_block(counters, k_ms, sm_mhz),
                     "kernel_ms": k_ms, "stage_ms": stage_ms, "per_rank_kernel_ms": [r[0] for r in per_rank],
                     "per_rank_stage_ms": [r[1:1 + len(stage_ms)] for r in per_rank], "traffic": None,
                     "traffic_source": "not captured for this workload"}

@@ -70,6 +70,7 @@ namespace dpg {
 constexpr int   kTile  = 32;            /* queries per warp (one per lane)                            */
 constexpr int   kGroup = DPGICP_GROUP;  /* points per bounding-box group of a searched cloud          */
 static_assert(kGroup == 8 || kGroup == 16 || kGroup == 32, "kGroup must be 8, 16 or 32");
+constexpr int   kSuper = 16;            /* groups per box of the upper level of the search hierarchy  */
 constexpr float kPad   = 1.0e30f;   /* coordinate of padded slots: any d2 against it is +inf      */
 constexpr double kScaleLin  = 4294967296.0;      /* 2^32 */
 constexpr double kScaleProd = 268435456.0;       /* 2^28 */
@@ -336,6 +337,8 @@ struct SmemLayout {
   float4 *tbox;     /* n_cap/kGroup group boxes of the target                                        */
   float4 *sbox;     /* n_cap/kGroup group boxes of the current source                                */
   float4 *stile;    /* n_cap/32 boxes of the source tiles (query boxes of the forward search)        */
+  float4 *tsup;     /* upper level: boxes of kSuper consecutive groups of the target ...             */
+  float4 *ssup;     /* ... and of the current source                                                 */
   int32_t *tcnt;    /* n_cap/32 accepted per source tile (rank for the covariance cap)              */
   long long *red;   /* 48 int64: [0..15] totals of the pass, [16..47] this CTA's totals by pass parity (clusters) */
   double *dpart;    /* dpart_bytes(warps): per-warp int64 partials of the pass (two parities) / 16 tile partials of
@@ -359,9 +362,12 @@ __host__ __device__ inline size_t dpart_bytes(int warps) {
   return pass > cov ? pass : cov;
 }
 
+__host__ __device__ inline int n_super_boxes(int n_groups) { return (n_groups + kSuper - 1) / kSuper; }
+
 __host__ __device__ inline size_t smem_bytes(int n_cap, bool projective, bool trim, int warps) {
   const int g = n_cap / kGroup, t = n_cap / kTile;
-  return (size_t)n_cap * (8 + 8 + 4) + (size_t)g * (16 + 16) + (size_t)t * (16 + 4) + 48 * 8 + dpart_bytes(warps) + 16 + 32 +
+  return (size_t)n_cap * (8 + 8 + 4) + (size_t)g * (16 + 16) + (size_t)t * (16 + 4) + (size_t)n_super_boxes(g) * (16 + 16) + 48 * 8 +
+         dpart_bytes(warps) + 16 + 32 +
          16 + 64 + 16 + (projective ? (size_t)n_cap * 8 : 0) + (trim ? (size_t)n_cap * 4 : 0);
 }
 
@@ -375,6 +381,8 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int n_cap, bool
   L.tbox = (float4 *)(base + o); o += (size_t)g * 16;
   L.sbox = (float4 *)(base + o); o += (size_t)g * 16;
   L.stile = (float4 *)(base + o); o += (size_t)t * 16;
+  L.tsup = (float4 *)(base + o); o += (size_t)n_super_boxes(g) * 16;
+  L.ssup = (float4 *)(base + o); o += (size_t)n_super_boxes(g) * 16;
   L.red = (long long *)(base + o); o += 48 * 8;
   L.dpart = (double *)(base + o);  o += dpart_bytes(warps);
   L.mbar = (uint64_t *)(base + o); o += 16;
@@ -428,6 +436,21 @@ __device__ __forceinline__ void store_tile_boxes(float2 p, bool valid, int tile,
   if (tb != nullptr && lane == 0) tb[tile] = t;
 }
 
+/* upper level of the hierarchy: box s covers groups [s * kSuper, (s + 1) * kSuper) — 256 consecutive points.  One warp
+ * per box: sixteen lanes hold a group box each, four warp-wide minima / maxima.  Called by all warps between two
+ * __syncthreads (group boxes complete -> upper boxes complete). */
+__device__ __forceinline__ void build_super_boxes(const float4 *gb, int n_groups, float4 *sup, int warp, int nw, int lane) {
+  const float inf = __int_as_float(0x7f800000);
+  const int n_sup = n_super_boxes(n_groups);
+  for (int sb = warp; sb < n_sup; sb += nw) {
+    const int g = sb * kSuper + lane;
+    float4 b = make_float4(inf, inf, -inf, -inf);
+    if (lane < kSuper && g < n_groups) b = gb[g];
+    b.x = warp_min(b.x); b.y = warp_min(b.y); b.z = warp_max(b.z); b.w = warp_max(b.w);
+    if (lane == 0) sup[sb] = b;
+  }
+}
+
 /* executed-work counters kept in registers by every warp, flushed once per CTA */
 struct SearchStats {
   unsigned scans = 0, tests = 0, window_evals = 0;   /* window_evals: per lane (projective search) */
@@ -440,6 +463,49 @@ struct SearchStats {
 __device__ __forceinline__ float below(float d2) {
   return d2 > 0.0f ? __int_as_float(__float_as_int(d2) - 1) : -1.0f;
 }
+
+/* Candidate rounds of the pruned searches, two levels: ONE lane-parallel round over the upper boxes (256 points each, at
+ * most 32 of them for DPGICP_MAX_POINTS), then per round the 2 x 16 groups of the next two surviving upper boxes — 2 to 3
+ * rounds for a 1081-point scan where a flat pass over the groups takes 3, 3 to 4 instead of 8 for 4096 points.  An upper
+ * box contains its groups' boxes and every operation of the lower bound is monotone, so its bound never exceeds
+ * theirs: nothing a flat pass would have kept is dropped.  Groups still come in ascending order.  The brute-force
+ * variant walks all groups, 32 per round.  Defines mask (bit b = group (b < 16 ? g0 : g1) + (b & 15)). */
+#define DPG_ROUNDS_BEGIN(QBOX, BMAX)                                                                                     \
+  int base__ = 0;                                                                                                        \
+  unsigned up__ = 0u;                                                                                                    \
+  if (PRUNED) {                                                                                                          \
+    const bool c__ = (lb_box_box(QBOX, lds128(a_sup + lane * 16)) <= (BMAX)) & (lane < n_super_boxes(n_groups));         \
+    up__ = __ballot_sync(0xffffffffu, c__);                                                                              \
+    ++st.tests;                                                                                                          \
+  }                                                                                                                      \
+  for (;;) {                                                                                                             \
+    unsigned mask;                                                                                                       \
+    int g0, g1;                                                                                                          \
+    if (PRUNED) {                                                                                                        \
+      if (!up__) break;                                                                                                  \
+      const int s0__ = __ffs(up__) - 1;                                                                                  \
+      up__ &= up__ - 1;                                                                                                  \
+      const bool two__ = up__ != 0u;                                                                                     \
+      const int s1__ = two__ ? __ffs(up__) - 1 : s0__;                                                                   \
+      up__ &= up__ - 1;                 /* 0 & anything = 0: harmless when there was no second box */                    \
+      g0 = s0__ * kSuper; g1 = s1__ * kSuper;                                                                            \
+      const int gl__ = (lane < kSuper ? g0 : g1) + (lane & (kSuper - 1));                                                \
+      const bool c__ = (lb_box_box(QBOX, lds128(a_boxes + gl__ * 16)) <= (BMAX)) & (gl__ < n_groups) &                   \
+                       ((lane < kSuper) | two__);                                                                        \
+      mask = __ballot_sync(0xffffffffu, c__);                                                                            \
+      ++st.tests;                                                                                                        \
+    } else {                                                                                                             \
+      if (base__ >= n_groups) break;                                                                                     \
+      const int rem__ = n_groups - base__;                                                                               \
+      mask = rem__ >= 32 ? 0xffffffffu : ((1u << rem__) - 1u);                                                           \
+      g0 = base__; g1 = base__ + kSuper;                                                                                 \
+      base__ += 32;                                                                                                      \
+    }
+#define DPG_ROUNDS_END }
+#define DPG_NEXT_GROUP(G)                                                                                                \
+      const int bit__ = __ffs(mask) - 1;                                                                                 \
+      mask &= mask - 1;                                                                                                  \
+      const int G = ((bit__ & kSuper) ? g1 : g0) + (bit__ & (kSuper - 1));
 
 /* ------------------------------------------------------------------------------------------------
  * Exact forward nearest neighbour of one query per lane over a grouped cloud in shared memory.
@@ -454,12 +520,12 @@ __device__ __forceinline__ float below(float d2) {
  * ---------------------------------------------------------------------------------------------- */
 template <bool PRUNED>
 __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
-                                           int n_groups, float qx, float qy, bool active, float4 qbox,
+                                           const float4 *__restrict__ sup, int n_groups, float qx, float qy, bool active, float4 qbox,
                                            float &bd, int &bj, bool seeded, SearchStats &st, float gate, int lane,
                                            float one) {
   const f32x2 one2 = pack2(one, one);
-  uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
-  DPG_KEEP_IN_REGISTER(a_cloud); DPG_KEEP_IN_REGISTER(a_boxes);
+  uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes), a_sup = smem_u32(sup);
+  DPG_KEEP_IN_REGISTER(a_cloud); DPG_KEEP_IN_REGISTER(a_boxes); DPG_KEEP_IN_REGISTER(a_sup);
   const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy);
   float thr = active ? (seeded ? below(bd) : bd) : -1.0f;
   float bmax = 0.0f;
@@ -468,25 +534,12 @@ __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, con
   st.searches++;
   if (bmax >= gate) st.loose++;
 #endif
-  for (int base = 0; base < n_groups; base += 32) {
-    unsigned mask;
-    if (PRUNED) {
-      const int g = base + lane;
-      /* no branch around the test: a lane past the last group reads whatever follows the boxes in this CTA's
-       * shared memory (at most 32 slots further, always inside the allocation) and is masked out */
-      const bool cand = (lb_box_box(qbox, lds128(a_boxes + g * 16)) <= bmax) & (g < n_groups);
-      mask = __ballot_sync(0xffffffffu, cand);
-      ++st.tests;
+  DPG_ROUNDS_BEGIN(qbox, bmax)
 #ifdef DPGICP_STATS
-      st.cands += __popc(mask);
+    if (PRUNED) st.cands += __popc(mask);
 #endif
-    } else {
-      const int rem = n_groups - base;
-      mask = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-    }
     while (mask) {
-      const int g = base + __ffs(mask) - 1;
-      mask &= mask - 1;
+      DPG_NEXT_GROUP(g)
       ++st.scans;
       const uint32_t a_grp = a_cloud + g * (kGroup * 8);
       float dd[kGroup];
@@ -513,7 +566,7 @@ __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, con
       /* groups come in ascending order: a tie with an earlier group's point (j > bj) never wins */
       if (gd <= thr && (gd < bd || j < bj)) { bd = gd; bj = j; thr = gd; }
     }
-  }
+  DPG_ROUNDS_END
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -524,11 +577,12 @@ __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, con
  * ---------------------------------------------------------------------------------------------- */
 template <bool PRUNED>
 __device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
-                                                 int n_groups, float qx, float qy, bool active, float4 qbox, float bd,
+                                                 const float4 *__restrict__ sup, int n_groups, float qx, float qy, bool active,
+                                                 float4 qbox, float bd,
                                                  SearchStats &st, int lane, float one) {
   const f32x2 one2 = pack2(one, one);
-  uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes);
-  DPG_KEEP_IN_REGISTER(a_cloud); DPG_KEEP_IN_REGISTER(a_boxes);
+  uint32_t a_cloud = smem_u32(cloud), a_boxes = smem_u32(boxes), a_sup = smem_u32(sup);
+  DPG_KEEP_IN_REGISTER(a_cloud); DPG_KEEP_IN_REGISTER(a_boxes); DPG_KEEP_IN_REGISTER(a_sup);
   const f32x2 q2 = pack2(qx, qy), qx2 = pack2(qx, qx), qy2 = pack2(qy, qy);
   float thr = active ? below(bd) : -1.0f;               /* -1: this lane needs nothing (any more; or bd = 0: nothing can be closer) */
   bool closer = false;
@@ -537,23 +591,12 @@ __device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ clou
 #ifdef DPGICP_STATS
   st.searches++;
 #endif
-  for (int base = 0; base < n_groups; base += 32) {
-    unsigned mask;
-    if (PRUNED) {
-      const int g = base + lane;
-      const bool cand = (lb_box_box(qbox, lds128(a_boxes + g * 16)) <= bmax) & (g < n_groups);
-      mask = __ballot_sync(0xffffffffu, cand);
-      ++st.tests;
+  DPG_ROUNDS_BEGIN(qbox, bmax)
 #ifdef DPGICP_STATS
-      st.cands += __popc(mask);
+    if (PRUNED) st.cands += __popc(mask);
 #endif
-    } else {
-      const int rem = n_groups - base;
-      mask = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-    }
     while (mask) {
-      const int g = base + __ffs(mask) - 1;
-      mask &= mask - 1;
+      DPG_NEXT_GROUP(g)
       if (PRUNED) {
         const bool need = lb_point_box(q2, lds128(a_boxes + g * 16)) <= thr;
         if (!__any_sync(0xffffffffu, need)) continue;
@@ -574,7 +617,7 @@ __device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ clou
 #undef DPG_SCAN2
       if (gd <= thr) { closer = true; thr = -1.0f; }    /* a strictly closer point: this lane is done */
     }
-  }
+  DPG_ROUNDS_END
   return closer;
 }
 
@@ -667,7 +710,7 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
     const float d0 = dist2(q.x, q.y, p.x, p.y);
     if (d0 <= gate) { bd = d0; bj = seed; seeded = true; }
   }
-  nn_forward<PRUNED>(L.tgt, L.tbox, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, seeded, st, gate, lane, one);
+  nn_forward<PRUNED>(L.tgt, L.tbox, L.tsup, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, seeded, st, gate, lane, one);
   fwd_ok = valid && (bj != 0x7fffffff);
   DPG_CHECK(!fwd_ok || (bj >= 0 && bj < n_groups_t * kGroup && bd <= gate));
   j_out = bj;
@@ -679,7 +722,7 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
     const float4 rbox = warp_box(r, fwd_ok);
     /* dist2(r, p) == dist2(p, r) bit for bit: fl(a-b) = -fl(b-a) and the square drops the sign, so source point i
      * itself is at exactly bd from r and "strictly closer than bd" is well defined */
-    const bool closer = nn_closer_exists<PRUNED>(L.src, L.sbox, n_groups_s, r.x, r.y, fwd_ok, rbox, bd, st, lane, one);
+    const bool closer = nn_closer_exists<PRUNED>(L.src, L.sbox, L.ssup, n_groups_s, r.x, r.y, fwd_ok, rbox, bd, st, lane, one);
     accept = fwd_ok && !closer;
   }
   return accept;
@@ -1146,6 +1189,11 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       }
     }
     __syncthreads();
+    if constexpr (SEARCH == DPGICP_SEARCH_PRUNED) {      /* upper level of the box hierarchy, from the complete group boxes */
+      build_super_boxes(L.tbox, gt, L.tsup, warp, nw, lane);
+      build_super_boxes(L.sbox, gs, L.ssup, warp, nw, lane);
+      __syncthreads();
+    }
 
     /* ---- parity hook: a single correspondence pass ------------------------------------------ */
     if (P.corr_out != nullptr) {
@@ -1354,6 +1402,10 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       __syncthreads();
       PH_MARK(5);                                     /* wait */
       if (stop) break;
+      if constexpr (SEARCH == DPGICP_SEARCH_PRUNED) {
+        build_super_boxes(L.sbox, gs, L.ssup, warp, nw, lane);
+        __syncthreads();
+      }
     }
 #ifdef DPGICP_PHASE_TIMING
     if (tid == 0)
@@ -1413,6 +1465,10 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
         }
         __syncthreads();
+        if constexpr (SEARCH == DPGICP_SEARCH_PRUNED) {
+          build_super_boxes(L.sbox, gs, L.ssup, warp, nw, lane);
+          __syncthreads();
+        }
         for (int tile = tile0; tile < ts; tile += tile_stride) {
           float2 q; int j; float d; bool fwd;
           const bool ok = match_any<SEARCH>(L, P, tile, ns, nt, gs, gt, q, j, d, fwd, stats);

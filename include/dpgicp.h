@@ -356,8 +356,9 @@ int  dpgicp_last_run_stage_ms(dpgicp_ctx *ctx, float stage_ms[8], int32_t *n_sta
  * the roofline of the distance loop: separately rounded FMUL+FADD (what the bit-exact loop may use)
  * and FFMA (for context).  Results in operations per second (one FMUL, FADD or FFMA = 1 op).     */
 int  dpgicp_fp32_probe(dpgicp_ctx *ctx, double *ops_per_s_mul_add, double *ops_per_s_fma);
-/* The same FMUL+FADD chains issued as packed pairs (sm_100 FMUL2 / FADD2, what the distance loop uses):
- * operations per second, one packed instruction = 2 operations.                                   */
+/* The same chains issued as packed pairs (sm_100 FMUL2 + the packed sum the distance loop uses): operations per
+ * second, one packed instruction = 2 operations.  Measured equal to the scalar rate: a packed instruction takes two
+ * pipe cycles, so packing saves issue slots, not FP32 time.                                         */
 int  dpgicp_fp32x2_probe(dpgicp_ctx *ctx, double *ops_per_s_mul_add_packed);
 
 #ifdef __cplusplus
