@@ -12,5 +12,5 @@ timeout 600 $CMD > gpurun_out/plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum,sm__inst_executed.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
 timeout 600 $CMD > gpurun_out/plain2.log 2>&1 &&
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:icp_pairs -s 12 -c 4 -o gpurun_out/prof_icp_v6 -f $CMD > gpurun_out/ncu_full.log 2>&1
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:icp_pairs -s 12 -c 4 -o gpurun_out/prof_icp_final -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
