@@ -39,3 +39,16 @@ def test_build_entry_point():
         assert os.path.exists(os.path.join(ROOT, rel)), rel
     if os.path.isdir("/root/reference/src/icp_cov"):
         assert os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdpgref.so"))
+
+
+def test_roofline_helpers_definitions():
+    """The two ceilings bench.py quotes: the FP32 peak is the LARGER of the two measured separately-rounded rates (scalar and
+    packed chains run at the same rate; the packed probe once reported twice that, from fused instructions) and the
+    shared-memory bound charges two write-back cycles per warp-level point evaluation."""
+    sys.path.insert(0, ROOT)
+    import bench
+    peak, scalar, packed = bench.fp32_peak({"mul_add_ops_per_s": 36.2e12, "mul_add_packed_ops_per_s": 37.1e12, "fma_ops_per_s": 36e12}, 37.2)
+    assert (peak, scalar, packed) == (37.1, 36.2, 37.1)
+    assert bench.fp32_peak({"mul_add_ops_per_s": 0.0}, 37.2)[0] == 37.2            # no probe: nominal rate
+    blk = bench.smem_block({"distance_evals": 32 * 1000}, k_ms=1.0, sm_mhz=1000.0, n_sm=2)
+    assert blk["busy_cycles_per_launch"] == 2000.0 and blk["available_cycles"] == 2.0e6 and blk["frac"] == 1e-3

@@ -146,6 +146,34 @@ def test_correspondence_ties_pick_lowest_index(gpu_matcher):
             assert np.array_equal(got, want), (search, rec)
 
 
+@pytest.mark.parametrize("n", [300, 1500, 4097, 8192])
+def test_box_hierarchy_on_large_unordered_clouds(gpu_matcher, n):
+    """The two-level candidate rounds of the pruned search (one round over 256-point boxes, then the groups of the
+    surviving ones, two upper boxes per round) against the brute-force walk and the oracle on clouds that are NOT in
+    beam order — loose boxes, many surviving upper boxes, several rounds — with lattice ties and duplicated points, at
+    sizes that leave the last upper box partly filled (300, 1500, 4097) and at the maximum (8192 = 32 upper boxes)."""
+    rng = np.random.default_rng(100 + n)
+    tgt = rng.uniform(0, 12, (n, 2))
+    tgt[: n // 4] = np.round(tgt[: n // 4] * 4) / 4                     # lattice points: exact ties
+    tgt[n // 4: n // 3] = tgt[rng.integers(0, n // 4, n // 3 - n // 4)]  # duplicates
+    tgt = tgt[rng.permutation(n)].astype(np.float32)
+    m = max(n - 37, 1)
+    src = (tgt[rng.permutation(n)[:m]] + rng.normal(0, 0.02, (m, 2))).astype(np.float32)
+    src[: m // 5] = tgt[rng.integers(0, n, m // 5)]                      # exact hits, zero distance
+    T = np.array([np.cos(0.01), np.sin(0.01), 0.02, -0.01], np.float32)
+    for rec in (1, 0):
+        for gate in (0.6, 0.05):
+            want = None
+            for search in (SEARCH_BRUTE, SEARCH_PRUNED):
+                p = Params.defaults(search=search, use_reciprocal=rec, max_correspondence_distance=gate)
+                got, got_d2 = gpu_matcher.correspondences(src, tgt, T, p)
+                if want is None:
+                    _, want, want_d2 = O.correspondences(O.transform_points(T, src), tgt, p)
+                assert np.array_equal(got, want), (n, rec, gate, search)
+                ok = want >= 0
+                assert np.array_equal(got_d2[ok].view(np.uint32), want_d2[ok].view(np.uint32)), (n, rec, gate, search)
+
+
 # ---- whole path: BASELINE configs at oracle-sized batches ---------------------------------------------------
 def test_config1_room_pair_default_params(gpu_matcher):
     wl = synth.config_room_pair()
