@@ -19,6 +19,14 @@
  *                             no tests or golden vectors for it.  The loop below restates PCL's
  *                             published algorithm as documented in SURVEY.md Appendix A and is
  *                             anchored on the reference's call sites (dpg_slam.cc:387-416,445).
+ *                             One half of it IS checked against the real thing: the neighbour search
+ *                             (orc_correspondences*) returns the indices, the binary32 squared
+ *                             distances and the reciprocal sets of a real FLANN KDTreeSingleIndex —
+ *                             the library PCL's KdTreeFLANN wraps; OpenCV's bundled copy is in this
+ *                             image — on the benchmark configs (tests/test_pcl_emulation.py).  The rigid
+ *                             step (Eigen's Umeyama / JacobiSVD) and the convergence glue stay
+ *                             restated-only and are cross-checked against an independent float32 SVD
+ *                             emulation of the whole loop (tests/pcl_emulation.py).
  *
  * The types of the public C ABI (include/dpgicp.h) are reused for parameters and results so the
  * parity tests compare like with like.

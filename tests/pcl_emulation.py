@@ -15,6 +15,31 @@ from scipy.spatial import cKDTree
 F = np.float32
 
 
+class FlannTree:
+    """Exact nearest neighbour through a REAL FLANN single kd-tree — OpenCV's bundled copy of the library PCL links
+    (pcl::KdTreeFLANN = flann::KDTreeSingleIndex, leaf size 15, L2 on float32 3-D points, exact search: PCL passes
+    checks = -1, eps = 0).  Returns FLANN's own neighbour choice (its order among exact ties is whatever its tree walk
+    yields) and FLANN's own binary32 squared distance."""
+
+    def __init__(self, pts3):
+        import cv2
+        self._pts = np.ascontiguousarray(pts3, F)
+        self._index = cv2.flann.Index(self._pts, dict(algorithm=4, leaf_max_size=15))     # FLANN_INDEX_KDTREE_SINGLE
+
+    def query(self, q3):
+        ind, d2 = self._index.knnSearch(np.ascontiguousarray(q3, F), 1, params=dict(checks=-1, eps=0.0, sorted=True))
+        return d2[:, 0].astype(F), ind[:, 0].astype(np.int64)
+
+
+class ScipyTree:
+    def __init__(self, pts3):
+        self._tree = cKDTree(np.asarray(pts3, np.float64))
+
+    def query(self, q3):
+        d, j = self._tree.query(np.asarray(q3, np.float64), k=1)
+        return None, j
+
+
 def guess_matrix(guess) -> np.ndarray:
     """dpg_slam.cc:374-378: Matrix4f from (dx, dy, dtheta); cos/sin of the float angle, stored as float."""
     g = np.asarray(guess, F)
@@ -50,9 +75,11 @@ def umeyama_float32(src3: np.ndarray, dst3: np.ndarray) -> np.ndarray:
     return T
 
 
-def icp(src_xy, tgt_xy, guess, max_iterations=500, eps=5e-9, max_dist=0.6, reciprocal=True, trace=None):
+def icp(src_xy, tgt_xy, guess, max_iterations=500, eps=5e-9, max_dist=0.6, reciprocal=True, trace=None, nn="scipy"):
     """-> dict(T (4x4 float32), converged, iterations, stop, n_corr, mse).  stop in {"iterations", "transform",
-    "abs_mse", "no_correspondences"}.  ``trace`` (a list) receives (final BEFORE the pass as (c, s, tx, ty), K) per pass."""
+    "abs_mse", "no_correspondences"}.  ``trace`` (a list) receives (final BEFORE the pass as (c, s, tx, ty), K) per pass.
+    ``nn``: "scipy" (cKDTree) or "flann" (OpenCV's FLANN single kd-tree: PCL's own neighbour library)."""
+    Tree = FlannTree if nn == "flann" else ScipyTree
     src = np.zeros((len(src_xy), 3), F)
     tgt = np.zeros((len(tgt_xy), 3), F)
     if len(src_xy):
@@ -64,18 +91,20 @@ def icp(src_xy, tgt_xy, guess, max_iterations=500, eps=5e-9, max_dist=0.6, recip
     out = dict(T=final, converged=False, iterations=0, stop="no_correspondences", n_corr=0, mse=0.0)
     if len(src) == 0 or len(tgt) == 0:
         return out
-    tree_t = cKDTree(tgt.astype(np.float64))                            # A.1: target tree built once
+    tree_t = Tree(tgt)                                                  # A.1: target tree built once
     max_d2 = np.float64(max_dist) * np.float64(max_dist)                # double threshold vs float distance (A.3-2)
     mse_prev = np.finfo(np.float64).max
     it = 0
     while True:
-        _, j = tree_t.query(cur.astype(np.float64), k=1)
+        d2_tree, j = tree_t.query(cur)
         diff = (cur - tgt[j]).astype(F)
         d2 = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1] + diff[:, 2] * diff[:, 2]).astype(F)   # FLANN L2_Simple
+        if d2_tree is not None:
+            d2 = d2_tree                                                # FLANN's own value (bit-equal, tested)
         ok = ~(d2.astype(np.float64) > max_d2)
         if reciprocal:
-            tree_s = cKDTree(cur.astype(np.float64))                    # rebuilt every iteration: the source moved
-            _, back = tree_s.query(tgt[j].astype(np.float64), k=1)
+            tree_s = Tree(cur)                                          # rebuilt every iteration: the source moved
+            _, back = tree_s.query(tgt[j])
             ok &= back == np.arange(len(cur))
         idx = np.nonzero(ok)[0]
         K = len(idx)

@@ -96,3 +96,76 @@ def test_oracle_loop_against_independent_pcl_emulation(name, make, divisor, n_sa
     assert all(r["k_final_equal"] for r in rows if r["it_oracle"] == r["it_emu"])
     # a flipped stop decision leaves at most the creep of the remaining sub-threshold steps (step size <= 7.1e-5 m each)
     assert s["max_d_final_m_flipped"] <= 1e-3 and s["max_d_final_rad_flipped"] <= 1e-4, s
+
+
+# ---- the neighbour search against a REAL FLANN kd-tree (OpenCV's bundled copy of the library PCL links) -------------
+def _xyz(a):
+    out = np.zeros((len(a), 3), np.float32)
+    out[:, :2] = a
+    return out
+
+
+FLANN_CASES = [
+    ("config2 corridor, divisor 1", lambda: synth.config_corridor(n_pairs=40, seed=3), 1),
+    ("config2 corridor, divisor 5", lambda: synth.config_corridor(n_pairs=40, seed=3), 5),
+    ("config3 loop closure, divisor 1", lambda: synth.config_loop_closure(n_pairs=40, n_scans=60, seed=5), 1),
+]
+
+
+@pytest.mark.parametrize("name,make,divisor", FLANN_CASES, ids=[c[0] for c in FLANN_CASES])
+def test_oracle_search_equals_flann_single_kdtree(name, make, divisor):
+    """K1 of the path IS FLANN in the reference (pcl::KdTreeFLANN, exact search, L2 on float32, SURVEY App. A.1/A.3-2).  The
+    oracle's forward neighbour and its binary32 squared distance against what a real FLANN KDTreeSingleIndex (leaf 15,
+    checks = -1, eps = 0) returns, at the first, an early, the middle and the last iterate of sampled pairs: the same
+    index wherever the minimum is unique (a differing index must be an exact binary32 tie — FLANN's order among those is
+    its tree walk's, the oracle's is the rule of include/dpgicp.h), and the SAME BITS for every distance: FLANN's L2
+    functor rounds each product and each sum separately, which is the arithmetic contract of DESIGN.md section 3.  The
+    reciprocal sets built from two FLANN trees (PCL determineReciprocalCorrespondences) equal the oracle's too."""
+    pytest.importorskip("cv2")
+    wl = make()
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    fwd_only = Params.defaults(downsample_divisor=divisor, use_reciprocal=0)
+    recip = Params.defaults(downsample_divisor=divisor, use_reciprocal=1)
+    n_q = n_tie = n_rec = 0
+    for k in range(0, wl.n_pairs, 5):
+        s, t = int(wl.src_idx[k]), int(wl.tgt_idx[k])
+        S, T = pts[off[s]:off[s + 1]][::divisor], pts[off[t]:off[t + 1]][::divisor]
+        _, iterates, _ = O.icp(S, T, wl.guess[k], recip, trace=True)
+        tree_t = E.FlannTree(_xyz(T))
+        for it in sorted(set([0, min(1, len(iterates) - 1), len(iterates) // 2, len(iterates) - 1])):
+            cur = O.transform_points(iterates[it], S)
+            _, want, want_d2 = O.correspondences(cur, T, fwd_only)
+            d2f, jf = tree_t.query(_xyz(cur))
+            gated = want >= 0
+            # every gated query: FLANN's distance has the oracle's bits; outside the gate FLANN's distance exceeds it
+            assert np.array_equal(d2f[gated].view(np.uint32), want_d2[gated].view(np.uint32)), (k, it)
+            assert np.all(d2f[~gated].astype(np.float64) > 0.36), (k, it)
+            differ = gated & (jf != want)
+            n_q += int(gated.sum())
+            n_tie += int(differ.sum())          # same distance bits (asserted above), another index: an exact tie
+            # reciprocal correspondences the way PCL forms them, from two FLANN trees
+            _, want_r, _ = O.correspondences(cur, T, recip)
+            _, back = E.FlannTree(_xyz(cur)).query(_xyz(T)[jf])
+            got_r = np.where((d2f.astype(np.float64) <= 0.36) & (back == np.arange(len(cur))), jf, -1)
+            # reciprocal sets: equal, except where an exact tie was walked differently (forward: counted above; backward:
+            # two source points at exactly the same distance from the matched target point)
+            n_tie += int((got_r != want_r).sum())
+            n_rec += int((want_r >= 0).sum())
+    print(f"\n[flann] {name}: {n_q} gated queries, {n_tie} exact ties resolved differently, {n_rec} reciprocal pairs compared")
+    assert n_q > 2000
+    assert n_tie <= 0.001 * n_q
+
+
+def test_emulation_with_flann_equals_emulation_with_ckdtree():
+    """The whole-loop emulation run on PCL's own neighbour library (FLANN) instead of scipy's kd-tree: same iterates, same
+    stop — the report in profiles/ therefore holds for a FLANN-backed PCL loop as well."""
+    pytest.importorskip("cv2")
+    wl = synth.config_corridor(n_pairs=30, seed=2)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    for k in range(0, wl.n_pairs, 6):
+        s, t = int(wl.src_idx[k]), int(wl.tgt_idx[k])
+        S, T = pts[off[s]:off[s + 1]][::5], pts[off[t]:off[t + 1]][::5]
+        a = E.icp(S, T, wl.guess[k], nn="scipy")
+        b = E.icp(S, T, wl.guess[k], nn="flann")
+        assert (a["iterations"], a["stop"], a["n_corr"]) == (b["iterations"], b["stop"], b["n_corr"]), k
+        assert np.array_equal(a["T"], b["T"]), k
