@@ -169,3 +169,23 @@ def test_emulation_with_flann_equals_emulation_with_ckdtree():
         b = E.icp(S, T, wl.guess[k], nn="flann")
         assert (a["iterations"], a["stop"], a["n_corr"]) == (b["iterations"], b["stop"], b["n_corr"]), k
         assert np.array_equal(a["T"], b["T"]), k
+
+
+def test_flann_on_exact_ties_same_distance_other_index():
+    """Where the minimum is NOT unique (a lattice: many exact binary32 ties) a real FLANN kd-tree returns the same
+    distance bits as the oracle but whichever minimiser its tree walk meets first — here a higher index than the
+    oracle's lowest-index choice in every differing query.  This is the freedom the tie rule of
+    include/dpgicp.h fixes; it can only matter for inputs with exact ties, which range scans do not produce."""
+    pytest.importorskip("cv2")
+    gx, gy = np.meshgrid(np.arange(12, dtype=np.float32) * 0.25, np.arange(9, dtype=np.float32) * 0.25)
+    tgt = np.stack([gx.ravel(), gy.ravel()], 1).astype(np.float32)
+    sx, sy = np.meshgrid(np.arange(23, dtype=np.float32) * 0.125, np.arange(17, dtype=np.float32) * 0.125)
+    src = np.stack([sx.ravel(), sy.ravel()], 1).astype(np.float32)
+    _, want, want_d2 = O.correspondences(src, tgt, Params.defaults(use_reciprocal=0))
+    d2f, jf = E.FlannTree(_xyz(tgt)).query(_xyz(src))
+    assert np.array_equal(d2f.view(np.uint32), want_d2.view(np.uint32))
+    differ = jf != want
+    assert differ.any() and np.all(jf[differ] > want[differ])
+    # the differing picks are minimisers too: same distance from the query, bit for bit
+    alt = ((src[differ] - tgt[jf[differ]]) ** 2).astype(np.float32)
+    assert np.array_equal((alt[:, 0] + alt[:, 1]).astype(np.float32).view(np.uint32), want_d2[differ].view(np.uint32))
