@@ -365,3 +365,43 @@ def test_cpp_runner_multi_context_writes_the_same_csv(tmp_path):
                                 "--out", str(out)], capture_output=True, text=True, timeout=300)
             assert r.returncode == 0, r.stderr
         assert a.read_text() == b.read_text()
+
+
+# ---- the CUDA search against a real FLANN kd-tree, first hand ------------------------------------------------------------
+@pytest.mark.parametrize("divisor", [1, 5])
+def test_cuda_correspondences_equal_a_real_flann_kdtree(gpu_matcher, divisor):
+    """dpgicp_correspondences (the exact pruned search) against OpenCV's bundled FLANN KDTreeSingleIndex — the index and the
+    exact search pcl::KdTreeFLANN runs — at several iterates of corridor and loop-closure pairs: the same forward neighbours,
+    the same binary32 squared distances, and the reciprocal sets PCL's determineReciprocalCorrespondences forms from two
+    such trees (north star: "correspondence index sets bit-exact given the same iterate")."""
+    pytest.importorskip("cv2")
+    import pcl_emulation as E
+
+    def xyz(a):
+        out = np.zeros((len(a), 3), np.float32)
+        out[:, :2] = a
+        return out
+
+    n_q = 0
+    for wl in (synth.config_corridor(n_pairs=12, seed=31), synth.config_loop_closure(n_pairs=12, n_scans=30, seed=32)):
+        pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+        for k in range(0, wl.n_pairs, 3):
+            s, t = int(wl.src_idx[k]), int(wl.tgt_idx[k])
+            S, T = pts[off[s]:off[s + 1]][::divisor], pts[off[t]:off[t + 1]][::divisor]
+            _, iterates, _ = O.icp(S, T, wl.guess[k], Params.defaults(downsample_divisor=1), trace=True)
+            tree_t = E.FlannTree(xyz(T))
+            for it in sorted(set([0, len(iterates) // 2, len(iterates) - 1])):
+                Tm = iterates[it]
+                cur = O.transform_points(Tm, S)
+                d2f, jf = tree_t.query(xyz(cur))
+                inside = d2f.astype(np.float64) <= 0.36
+                got, got_d2 = gpu_matcher.correspondences(S, T, Tm, Params.defaults(use_reciprocal=0))
+                assert np.array_equal(got >= 0, inside), (k, it)
+                assert np.array_equal(got[inside], jf[inside]), (k, it)
+                assert np.array_equal(got_d2[inside].view(np.uint32), d2f[inside].view(np.uint32)), (k, it)
+                _, back = E.FlannTree(xyz(cur)).query(xyz(T)[jf])
+                want_r = np.where(inside & (back == np.arange(len(cur))), jf, -1)
+                got_r, _ = gpu_matcher.correspondences(S, T, Tm, Params.defaults(use_reciprocal=1))
+                assert np.array_equal(got_r, want_r), (k, it)
+                n_q += int(inside.sum())
+    assert n_q > 3000
