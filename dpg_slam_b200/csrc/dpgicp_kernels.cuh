@@ -71,6 +71,7 @@ constexpr int   kTile  = 32;            /* queries per warp (one per lane)      
 constexpr int   kGroup = DPGICP_GROUP;  /* points per bounding-box group of a searched cloud          */
 static_assert(kGroup == 8 || kGroup == 16 || kGroup == 32, "kGroup must be 8, 16 or 32");
 constexpr int   kSuper = 16;            /* groups per box of the upper level of the search hierarchy  */
+static_assert(DPGICP_MAX_POINTS / (kGroup * kSuper) <= 32, "the upper level is tested in ONE lane-parallel round: at most 32 boxes");
 constexpr float kPad   = 1.0e30f;   /* coordinate of padded slots: any d2 against it is +inf      */
 constexpr double kScaleLin  = 4294967296.0;      /* 2^32 */
 constexpr double kScaleProd = 268435456.0;       /* 2^28 */
