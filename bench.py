@@ -498,7 +498,7 @@ def measure_host_list(cx: Ctx, sm, name, search, wl, n_global, steps, warmup, wi
         for _ in range(0 if big else 3):      # big batches: everything is warm already and one e2e step takes seconds
             step_e2e()
         cx.barrier()
-        e2e_steps = 1 if big else max(3, min(steps, 10))
+        e2e_steps = 1 if big else max(3, min(2 * steps, 40))      # host-clocked: enough steps that one scheduling hiccup does not show
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             step_e2e()
