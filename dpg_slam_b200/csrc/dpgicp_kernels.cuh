@@ -17,14 +17,17 @@
  * independent, so any thread layout gives the same bits), binary64 closed-form planar step.
  *
  * Exact pruned search: points of a scan are in beam order, so kGroup (16) consecutive points form a
- * spatially compact group with an axis-aligned bounding box.  A warp handles a tile of 32 consecutive
- * queries (one per lane); box-to-box lower bounds (evaluated lane-parallel over groups) select
- * the groups that can still beat the tile's current bound, which is seeded with the previous
- * iteration's neighbour.  Lower bounds use the same rounding sequence as the distance itself, so
- * by monotonicity of rounding they never exceed a computed distance: pruning is exact, no
- * epsilons.  SEARCH_BRUTE scans every group through the same code.  A group's 16 distances are
- * packed FADD2 / FMUL2 pairs (3 issue slots per distance), their minimum a tree of three-input
- * minima; the index of the minimum is looked up only when a lane can improve or tie.
+ * spatially compact group with an axis-aligned bounding box, and kSuper (16) consecutive groups an
+ * upper-level box.  A warp handles a tile of 32 consecutive queries (one per lane); box-to-box
+ * lower bounds, evaluated lane-parallel first over the upper boxes and then over the groups of the
+ * surviving ones, select the groups that can still beat the tile's current bound, which is seeded
+ * with the previous iteration's neighbour.  Lower bounds use the same rounding sequence as the
+ * distance itself, so by monotonicity of rounding they never exceed a computed distance: pruning
+ * is exact, no epsilons.  SEARCH_BRUTE scans every group through the same code.  In shared memory a
+ * cloud is pair-interleaved — (x0, x1, y0, y1) per 16-byte word — so that the two distances of one
+ * LDS.128 are five packed instructions (FADD2 FADD2 FMUL2 FMUL2 + the individually rounded packed
+ * sum), their minimum a tree of three-input minima; the index of the minimum is looked up only when
+ * a lane can strictly improve on its seed (sticky tie rule, include/dpgicp.h).
  * SEARCH_PROJECTIVE (north-star extension, approximate): every lane locates its query in the other
  * scan's beam order by bisection over bearing keys and scans a window around it; defined by the oracle.
  *
