@@ -354,6 +354,21 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
       shapes[n_stages++] = {w, cs};
     }
   }
+  /* Small batches (the online caller's handful of pairs, a single runIcp-shaped call): a stage whose WHOLE batch is within
+   * the hand-over bound towards the next stage would see its queue dry at once and suspend every pair after its first
+   * pass — a launch, a state round trip through HBM and a re-staging for nothing.  Start the chain at the first stage that
+   * would keep its pairs (the last one at the latest). */
+  while (n_stages > 1 && ctx->handover_factor > 0.0) {
+    int next_units = -1;
+    KernelParams kq = kp;
+    kq.resume = 1;
+    int rcq = launch_stage(ctx, search, shapes[1].warps, shapes[1].csize, kq, smem_of(shapes[1].warps), (int64_t)1 << 40, &next_units);
+    if (rcq) return rcq;
+    const long long bound = (long long)std::ceil((shapes[1].csize > 1 ? ctx->handover_cluster : ctx->handover_factor) * (double)next_units);
+    if (count > bound) break;
+    for (int k = 1; k < n_stages; ++k) shapes[k - 1] = shapes[k];
+    --n_stages;
+  }
   CU_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, 32 * sizeof(unsigned long long), ctx->stream));
   int grid_prev = 0;
   const bool timing = ctx->stage_timing && corr_out == nullptr;

@@ -405,3 +405,27 @@ def test_cuda_correspondences_equal_a_real_flann_kdtree(gpu_matcher, divisor):
                 assert np.array_equal(got_r, want_r), (k, it)
                 n_q += int(inside.sum())
     assert n_q > 3000
+
+
+def test_small_batches_start_at_the_stage_that_keeps_them(gpu_matcher):
+    """A single runIcp-shaped call and the online caller's handful of pairs run as ONE launch of the widest fitting shape (no
+    stage that would suspend every pair after its first pass), with the records of the staged chain: the same pairs inside a
+    batch large enough to start at the narrow stage give identical bits."""
+    wl = synth.config_corridor(n_pairs=1200, seed=41)
+    pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
+    for p in (Params.defaults(), Params.defaults(downsample_divisor=1, cov_mode=COV_CENSI_CORR)):
+        gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+        big = gpu_matcher.submit_pairs(wl.src_idx, wl.tgt_idx, wl.guess, p)
+        n_big = gpu_matcher.last_run_counters()["kernel_launches"]
+        for k in (0, 7, 300):
+            s, t = int(wl.src_idx[k]), int(wl.tgt_idx[k])
+            before = gpu_matcher.last_run_counters()["kernel_launches"]
+            _, _, _, r = gpu_matcher.run_icp(pts[off[t]:off[t + 1]], pts[off[s]:off[s + 1]], wl.guess[k], p)
+            assert gpu_matcher.last_run_counters()["kernel_launches"] - before == 1
+            assert (r.tx, r.ty, r.iterations, r.status, r.mse) == (big["tx"][k], big["ty"][k], big["iterations"][k], big["status"][k], big["mse"][k])
+        gpu_matcher.upload_ranges(wl.ranges, wl.scanner)
+        before = gpu_matcher.last_run_counters()["kernel_launches"]
+        few = gpu_matcher.submit_pairs(wl.src_idx[:20], wl.tgt_idx[:20], wl.guess[:20], p)
+        assert gpu_matcher.last_run_counters()["kernel_launches"] - before == 1
+        assert few.tobytes() == big[:20].tobytes()
+        assert n_big >= 1
