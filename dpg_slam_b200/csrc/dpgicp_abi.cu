@@ -256,6 +256,7 @@ int launch_icp_w(dpgicp_ctx *ctx, int nw, int csize, const KernelParams &kp, siz
 int launch_stage(dpgicp_ctx *ctx, int search, int nw, int csize, const KernelParams &kp, size_t smem, int64_t n, int *grid_out) {
   if (search == DPGICP_SEARCH_PROJECTIVE) return launch_icp_w<DPGICP_SEARCH_PROJECTIVE>(ctx, nw, csize, kp, smem, n, grid_out);
   if (search == DPGICP_SEARCH_PRUNED) return launch_icp_w<DPGICP_SEARCH_PRUNED>(ctx, nw, csize, kp, smem, n, grid_out);
+  if (search == kSearchPrunedFlat) return launch_icp_w<kSearchPrunedFlat>(ctx, nw, csize, kp, smem, n, grid_out);
   return launch_icp_w<DPGICP_SEARCH_BRUTE>(ctx, nw, csize, kp, smem, n, grid_out);
 }
 
@@ -326,7 +327,8 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   const bool trim = p->outlier_mode != DPGICP_OUTLIER_NONE;
   /* shared memory of a stage: the reduction scratch grows with the CTA width */
   auto smem_of = [&](int warps) { return smem_bytes(n_cap, p->search == DPGICP_SEARCH_PROJECTIVE, trim, warps); };
-  const int search = p->search;
+  /* clouds of at most 32 groups: the pruned search's flat instantiation (one candidate round, no upper box level) */
+  const int search = (p->search == DPGICP_SEARCH_PRUNED && n_cap / kGroup <= kFlatMaxGroups) ? kSearchPrunedFlat : p->search;
 
   /* stage widths (warps per pair): narrow CTAs for the bulk of the batch, wider ones for the pairs
    * still running when a stage's queue runs dry; each width is balanced against the tile count */

@@ -73,6 +73,11 @@ namespace dpg {
 constexpr int   kTile  = 32;            /* queries per warp (one per lane)                            */
 constexpr int   kGroup = DPGICP_GROUP;  /* points per bounding-box group of a searched cloud          */
 static_assert(kGroup == 8 || kGroup == 16 || kGroup == 32, "kGroup must be 8, 16 or 32");
+/* internal instantiation of DPGICP_SEARCH_PRUNED for clouds of at most 32 groups (512 points — the reference's
+ * down-sampled scans): all groups fit ONE lane-parallel round, so no upper box level is built or tested.  A compile-time
+ * variant because a run-time branch in the candidate rounds cost the 1081-point batches 1.4 % (measured). */
+constexpr int   kSearchPrunedFlat = 3;
+constexpr int   kFlatMaxGroups = 32;
 constexpr int   kSuper = 16;            /* groups per box of the upper level of the search hierarchy  */
 static_assert(DPGICP_MAX_POINTS / (kGroup * kSuper) <= 32, "the upper level is tested in ONE lane-parallel round: at most 32 boxes");
 constexpr float kPad   = 1.0e30f;   /* coordinate of padded slots: any d2 against it is +inf      */
@@ -473,11 +478,12 @@ __device__ __forceinline__ float below(float d2) {
  * rounds for a 1081-point scan where a flat pass over the groups takes 3, 3 to 4 instead of 8 for 4096 points.  An upper
  * box contains its groups' boxes and every operation of the lower bound is monotone, so its bound never exceeds
  * theirs: nothing a flat pass would have kept is dropped.  Groups still come in ascending order.  The brute-force
- * variant walks all groups, 32 per round.  Defines mask (bit b = group (b < 16 ? g0 : g1) + (b & 15)). */
+ * variant walks all groups, 32 per round.  FLAT (kSearchPrunedFlat): a cloud of at most 32 groups is tested in one flat
+ * round and needs no upper level.  Defines mask (bit b = group (b < 16 ? g0 : g1) + (b & 15)). */
 #define DPG_ROUNDS_BEGIN(QBOX, BMAX)                                                                                     \
   int base__ = 0;                                                                                                        \
   unsigned up__ = 0u;                                                                                                    \
-  if (PRUNED) {                                                                                                          \
+  if (PRUNED && !FLAT) {                                                                                                 \
     const bool c__ = (lb_box_box(QBOX, lds128(a_sup + lane * 16)) <= (BMAX)) & (lane < n_super_boxes(n_groups));         \
     up__ = __ballot_sync(0xffffffffu, c__);                                                                              \
     ++st.tests;                                                                                                          \
@@ -485,7 +491,14 @@ __device__ __forceinline__ float below(float d2) {
   for (;;) {                                                                                                             \
     unsigned mask;                                                                                                       \
     int g0, g1;                                                                                                          \
-    if (PRUNED) {                                                                                                        \
+    if (PRUNED && FLAT) {                                                                                                \
+      if (base__) break;                                                                                                 \
+      base__ = 1;                                                                                                        \
+      g0 = 0; g1 = kSuper;                                                                                               \
+      const bool c__ = (lb_box_box(QBOX, lds128(a_boxes + lane * 16)) <= (BMAX)) & (lane < n_groups);                    \
+      mask = __ballot_sync(0xffffffffu, c__);                                                                            \
+      ++st.tests;                                                                                                        \
+    } else if (PRUNED) {                                                                                                 \
       if (!up__) break;                                                                                                  \
       const int s0__ = __ffs(up__) - 1;                                                                                  \
       up__ &= up__ - 1;                                                                                                  \
@@ -522,7 +535,7 @@ __device__ __forceinline__ float below(float d2) {
  *   (the steady state of ICP) it never does.
  *   `qbox` is the bounding box of the active lanes' queries.  PRUNED = false scans every group.
  * ---------------------------------------------------------------------------------------------- */
-template <bool PRUNED>
+template <bool PRUNED, bool FLAT>
 __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
                                            const float4 *__restrict__ sup, int n_groups, float qx, float qy, bool active, float4 qbox,
                                            float &bd, int &bj, bool seeded, SearchStats &st, float gate, int lane,
@@ -579,7 +592,7 @@ __device__ __forceinline__ void nn_forward(const float2 *__restrict__ cloud, con
  * asking for scans.  A per-lane point-to-box test and a warp vote in front of every candidate group's scan skip the
  * groups no lane can use (21 % of the candidates, measured).
  * ---------------------------------------------------------------------------------------------- */
-template <bool PRUNED>
+template <bool PRUNED, bool FLAT>
 __device__ __forceinline__ bool nn_closer_exists(const float2 *__restrict__ cloud, const float4 *__restrict__ boxes,
                                                  const float4 *__restrict__ sup, int n_groups, float qx, float qy, bool active,
                                                  float4 qbox, float bd,
@@ -694,7 +707,7 @@ __device__ __forceinline__ bool match_tile_projective(const SmemLayout &L, int t
   return accept;
 }
 
-template <bool PRUNED>
+template <bool PRUNED, bool FLAT>
 __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns, int n_groups_s,
                                            int n_groups_t, float gate, bool reciprocal, float one, float2 &q,
                                            int &j_out, float &d_out, bool &fwd_ok, SearchStats &st) {
@@ -714,7 +727,7 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
     const float d0 = dist2(q.x, q.y, p.x, p.y);
     if (d0 <= gate) { bd = d0; bj = seed; seeded = true; }
   }
-  nn_forward<PRUNED>(L.tgt, L.tbox, L.tsup, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, seeded, st, gate, lane, one);
+  nn_forward<PRUNED, FLAT>(L.tgt, L.tbox, L.tsup, n_groups_t, q.x, q.y, valid, L.stile[tile], bd, bj, seeded, st, gate, lane, one);
   fwd_ok = valid && (bj != 0x7fffffff);
   DPG_CHECK(!fwd_ok || (bj >= 0 && bj < n_groups_t * kGroup && bd <= gate));
   j_out = bj;
@@ -726,7 +739,7 @@ __device__ __forceinline__ bool match_tile(const SmemLayout &L, int tile, int ns
     const float4 rbox = warp_box(r, fwd_ok);
     /* dist2(r, p) == dist2(p, r) bit for bit: fl(a-b) = -fl(b-a) and the square drops the sign, so source point i
      * itself is at exactly bd from r and "strictly closer than bd" is well defined */
-    const bool closer = nn_closer_exists<PRUNED>(L.src, L.sbox, L.ssup, n_groups_s, r.x, r.y, fwd_ok, rbox, bd, st, lane, one);
+    const bool closer = nn_closer_exists<PRUNED, FLAT>(L.src, L.sbox, L.ssup, n_groups_s, r.x, r.y, fwd_ok, rbox, bd, st, lane, one);
     accept = fwd_ok && !closer;
   }
   return accept;
@@ -741,7 +754,7 @@ __device__ __forceinline__ bool match_any(const SmemLayout &L, const KP &P, int 
     return match_tile_projective(L, tile, ns, nt, P.gate, P.use_reciprocal != 0, P.proj_window, P.sensor_x, P.sensor_y, q, j,
                                  d, fwd, st);
   else
-    return match_tile<SEARCH == DPGICP_SEARCH_PRUNED>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, P.one, q, j, d, fwd, st);
+    return match_tile<SEARCH == DPGICP_SEARCH_PRUNED || SEARCH == kSearchPrunedFlat, SEARCH == kSearchPrunedFlat>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, P.one, q, j, d, fwd, st);
 }
 
 /* ------------------------------------------------------------------------------------------------
