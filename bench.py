@@ -685,6 +685,18 @@ def run_product_host_list(args):
             rec_h = sm.fetch_results()
             assert rec_h.tobytes() == rec_local.tobytes(), "records changed with cost hints (they may only change the schedule)"
             sm.set_pair_cost_hints(None)
+            # the same batch with the REFERENCE'S OWN settings (parameters.h:402 down-sampling by 5 -> 217 points, the live
+            # diagonal covariance of cov.h:572-575): what a drop-in caller that changes nothing runs
+            from dpg_slam_b200._abi import Params as _P
+            p_ref = _P.defaults()
+            for _ in range(3):
+                sm.run(p_ref)
+            r_ms, _ = cx.timed_steps(lambda: sm.run(p_ref), args.steps)
+            rec_r = sm.fetch_results()
+            ref_defaults = {"value": n_global * args.steps / (r_ms * 1e-3), "unit": UNIT, "ms_per_step": r_ms / args.steps,
+                            "mean_iterations": float(rec_r["iterations"].mean()),
+                            "what": "the corridor batch with dpgicp_default_params() = the reference's parameters.h values (divisor 5: "
+                                    "217-point clouds, max 500 iterations, reciprocal, live covariance), resident"}
             hinted = {"value": n_global * args.steps / (h_ms * 1e-3), "unit": UNIT, "ms_per_step": h_ms / args.steps,
                       "records_equal_unhinted": True,
                       "what": "the same resident batch re-aligned with the previous alignment's iteration counts as cost hints "
@@ -707,7 +719,8 @@ def run_product_host_list(args):
                                              "roofline": {k_: roof2[k_] for k_ in ("achieved", "peak", "frac", "algorithmic_speedup", "kernel_ms", "stage_ms")},
                                              "oracle_sample_bit_equal": {"sample": int(len(k)), "bit_equal": bool(same)},
                                              "mean_iterations": float(rec2["iterations"].mean())},
-                            "corridor_realigned_with_cost_hints": hinted}
+                            "corridor_realigned_with_cost_hints": hinted,
+                            "corridor_reference_default_params": ref_defaults}
         if world == 1 and rank == 0 and not args.no_latency:
             line["latency"] = latency_block(sm)                  # last: it replaces the scan store
     if rank == 0:
