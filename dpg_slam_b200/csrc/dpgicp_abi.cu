@@ -257,6 +257,8 @@ int launch_stage(dpgicp_ctx *ctx, int search, int nw, int csize, const KernelPar
   if (search == DPGICP_SEARCH_PROJECTIVE) return launch_icp_w<DPGICP_SEARCH_PROJECTIVE>(ctx, nw, csize, kp, smem, n, grid_out);
   if (search == DPGICP_SEARCH_PRUNED) return launch_icp_w<DPGICP_SEARCH_PRUNED>(ctx, nw, csize, kp, smem, n, grid_out);
   if (search == kSearchPrunedFlat) return launch_icp_w<kSearchPrunedFlat>(ctx, nw, csize, kp, smem, n, grid_out);
+  if (search == kSearchPrunedStock) return launch_icp_w<kSearchPrunedStock>(ctx, nw, csize, kp, smem, n, grid_out);
+  if (search == kSearchPrunedFlatStock) return launch_icp_w<kSearchPrunedFlatStock>(ctx, nw, csize, kp, smem, n, grid_out);
   return launch_icp_w<DPGICP_SEARCH_BRUTE>(ctx, nw, csize, kp, smem, n, grid_out);
 }
 
@@ -328,7 +330,13 @@ int launch_icp(dpgicp_ctx *ctx, const Store &st, const Batch &b, const dpgicp_pa
   /* shared memory of a stage: the reduction scratch grows with the CTA width */
   auto smem_of = [&](int warps) { return smem_bytes(n_cap, p->search == DPGICP_SEARCH_PROJECTIVE, trim, warps); };
   /* clouds of at most 32 groups: the pruned search's flat instantiation (one candidate round, no upper box level) */
-  const int search = (p->search == DPGICP_SEARCH_PRUNED && n_cap / kGroup <= kFlatMaxGroups) ? kSearchPrunedFlat : p->search;
+  int search = p->search;
+  if (search == DPGICP_SEARCH_PRUNED) {
+    /* ... and the stock configuration's: point-to-point, no rejector, no parity hook */
+    const bool stock = p->metric == DPGICP_METRIC_POINT_TO_POINT && !trim && corr_out == nullptr && corr_seed == nullptr;
+    const bool flat = n_cap / kGroup <= kFlatMaxGroups;
+    search = stock ? (flat ? kSearchPrunedFlatStock : kSearchPrunedStock) : (flat ? kSearchPrunedFlat : DPGICP_SEARCH_PRUNED);
+  }
 
   /* stage widths (warps per pair): narrow CTAs for the bulk of the batch, wider ones for the pairs
    * still running when a stage's queue runs dry; each width is balanced against the tile count */

@@ -78,6 +78,14 @@ static_assert(kGroup == 8 || kGroup == 16 || kGroup == 32, "kGroup must be 8, 16
  * variant because a run-time branch in the candidate rounds cost the 1081-point batches 1.4 % (measured). */
 constexpr int   kSearchPrunedFlat = 3;
 constexpr int   kFlatMaxGroups = 32;
+/* ... and of the stock configuration — point-to-point metric, no outlier rejector, no parity hook — with those run-time
+ * branches compiled out of the pass loop (+1 % on the 1081-point batches, measured): the pruned search, plain and flat */
+constexpr int   kSearchPrunedStock = 4;
+constexpr int   kSearchPrunedFlatStock = 5;
+__host__ __device__ constexpr bool search_is_projective(int s) { return s == DPGICP_SEARCH_PROJECTIVE; }
+__host__ __device__ constexpr bool search_is_flat(int s) { return s == kSearchPrunedFlat || s == kSearchPrunedFlatStock; }
+__host__ __device__ constexpr bool search_is_pruned(int s) { return s == DPGICP_SEARCH_PRUNED || s >= kSearchPrunedFlat; }
+__host__ __device__ constexpr bool search_is_stock(int s) { return s == kSearchPrunedStock || s == kSearchPrunedFlatStock; }
 constexpr int   kSuper = 16;            /* groups per box of the upper level of the search hierarchy  */
 static_assert(DPGICP_MAX_POINTS / (kGroup * kSuper) <= 32, "the upper level is tested in ONE lane-parallel round: at most 32 boxes");
 constexpr float kPad   = 1.0e30f;   /* coordinate of padded slots: any d2 against it is +inf      */
@@ -750,11 +758,11 @@ struct KernelParams;
 template <int SEARCH, typename KP>
 __device__ __forceinline__ bool match_any(const SmemLayout &L, const KP &P, int tile, int ns, int nt, int gs, int gt,
                                           float2 &q, int &j, float &d, bool &fwd, SearchStats &st) {
-  if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE)
+  if constexpr (search_is_projective(SEARCH))
     return match_tile_projective(L, tile, ns, nt, P.gate, P.use_reciprocal != 0, P.proj_window, P.sensor_x, P.sensor_y, q, j,
                                  d, fwd, st);
   else
-    return match_tile<SEARCH == DPGICP_SEARCH_PRUNED || SEARCH == kSearchPrunedFlat, SEARCH == kSearchPrunedFlat>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, P.one, q, j, d, fwd, st);
+    return match_tile<search_is_pruned(SEARCH), search_is_flat(SEARCH)>(L, tile, ns, gs, gt, P.gate, P.use_reciprocal != 0, P.one, q, j, d, fwd, st);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -903,11 +911,11 @@ __device__ __forceinline__ long long fxp(double v) { return __double2ll_rn(__dmu
  * accumulate_normal_eq term for term.
  * ---------------------------------------------------------------------------------------------- */
 template <typename KP>
-__device__ __forceinline__ void accumulate_pair(const SmemLayout &L, const KP &P, float2 q, int j, float d, int nt,
+__device__ __forceinline__ void accumulate_pair(const SmemLayout &L, const KP &P, bool p2l, float2 q, int j, float d, int nt,
                                                 long long (&m)[10], int &m_k) {
   const float2 t = ld_pt(L.tgt, j);
   const double px = q.x, py = q.y, qx = t.x, qy = t.y;
-  if (P.metric == DPGICP_METRIC_POINT_TO_LINE) {
+  if (p2l) {
     /* line through the matched target point and its closer beam neighbour (oracle:
      * accumulate_normal_eq); m0..m5 = A (11,12,13,22,23,33), m6..m8 = sum J^T r */
     int j2 = -1;
@@ -1090,7 +1098,7 @@ __device__ __forceinline__ T *peer_smem(T *p, int rank) {
 template <int WARPS, int SEARCH, int CSIZE>
 __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(const KernelParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemLayout L = carve(smem_raw, P.n_cap, SEARCH == DPGICP_SEARCH_PROJECTIVE, (int)(blockDim.x >> 5));
+  SmemLayout L = carve(smem_raw, P.n_cap, search_is_projective(SEARCH), (int)(blockDim.x >> 5));
   int tid = threadIdx.x;
   DPG_KEEP_IN_REGISTER(tid);
   int lane = tid & 31;
@@ -1106,7 +1114,9 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
   const int div = P.divisor;
   constexpr int GPT = kTile / kGroup;        /* groups per tile */
   uint32_t mbar_phase = 0;
-  const bool trim = (CSIZE == 1) && P.outlier_mode != DPGICP_OUTLIER_NONE;   /* the host never combines it with clusters */
+  constexpr bool STOCK = search_is_stock(SEARCH);      /* point-to-point, no rejector, no parity hook: the host's promise */
+  const bool trim = !STOCK && (CSIZE == 1) && P.outlier_mode != DPGICP_OUTLIER_NONE;   /* the host never combines it with clusters */
+  const bool p2l = !STOCK && P.metric == DPGICP_METRIC_POINT_TO_LINE;
 
   if (tid == 0) mbar_init(L.mbar, 1);
   __syncthreads();
@@ -1175,7 +1185,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       const float2 p = k < nt ? L.tgt[k] : make_float2(kPad, kPad);
       __syncwarp();
       st_pt(L.tgt, k, p);
-      if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) L.tkey[k] = beam_key(p.x, p.y, P.sensor_x, P.sensor_y);
+      if constexpr (search_is_projective(SEARCH)) L.tkey[k] = beam_key(p.x, p.y, P.sensor_x, P.sensor_y);
       else store_tile_boxes(p, k < nt, t, L.tbox, nullptr, lane);
     }
     for (int t = warp; t < ts; t += nw) {
@@ -1183,7 +1193,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       float2 p = make_float2(kPad, kPad);
       if (k < ns) p = P.resume ? ld_pt(L.src, k) : L.src[k];
       __syncwarp();
-      if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) {
+      if constexpr (search_is_projective(SEARCH)) {
         /* keys of the UNTRANSFORMED source (a resumed pair holds the current one: take the original from the store) */
         float2 o = p;
         if (P.resume && k < ns) o = __ldg(srow + (size_t)k * div);
@@ -1191,12 +1201,12 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       }
       if (!P.resume) {
         if (k < ns) p = xform(task.c, task.s, task.tx, task.ty, p);
-        L.nn[k] = (P.corr_seed != nullptr && k < ns) ? P.corr_seed[k] : -1;
+        L.nn[k] = (!STOCK && P.corr_seed != nullptr && k < ns) ? P.corr_seed[k] : -1;
       }
       if (!P.resume || k >= ns) st_pt(L.src, k, p);
-      if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
+      if constexpr (!search_is_projective(SEARCH)) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
     }
-    if (SEARCH == DPGICP_SEARCH_PROJECTIVE && tid == 0) {
+    if (search_is_projective(SEARCH) && tid == 0) {
       /* accumulated transform the source in shared memory has been moved by so far */
       if (P.resume) {
         const SuspHeader h = *reinterpret_cast<const SuspHeader *>(slot_in);
@@ -1206,14 +1216,14 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       }
     }
     __syncthreads();
-    if constexpr (SEARCH == DPGICP_SEARCH_PRUNED) {      /* upper level of the box hierarchy, from the complete group boxes */
+    if constexpr (search_is_pruned(SEARCH) && !search_is_flat(SEARCH)) {      /* upper level of the box hierarchy, from the complete group boxes */
       build_super_boxes(L.tbox, gt, L.tsup, warp, nw, lane);
       build_super_boxes(L.sbox, gs, L.ssup, warp, nw, lane);
       __syncthreads();
     }
 
     /* ---- parity hook: a single correspondence pass ------------------------------------------ */
-    if (P.corr_out != nullptr) {
+    if (!STOCK && P.corr_out != nullptr) {
       for (int tile = warp; tile < ts; tile += nw) {
         float2 q; int j; float d; bool fwd;
         const bool acc = match_any<SEARCH>(L, P, tile, ns, nt, gs, gt, q, j, d, fwd, stats);
@@ -1282,7 +1292,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           const float2 q = ld_pt(L.src, i);
           const float2 t = ld_pt(L.tgt, v);
           const float d = dist2(q.x, q.y, t.x, t.y);          /* the search's own value: same operands, same roundings */
-          if (!trim || d <= tau) accumulate_pair(L, P, q, v, d, nt, m, m_k);
+          if (!trim || d <= tau) accumulate_pair(L, P, p2l, q, v, d, nt, m, m_k);
         }
       }
       PH_MARK(0);                                     /* own tiles */
@@ -1349,12 +1359,12 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
         if (K < 3) {                                   /* App. A.3-4 */
           status |= DPGICP_STOP_NO_CORRESPONDENCES;
           st = 2;
-        } else if (P.metric == DPGICP_METRIC_POINT_TO_LINE && !solve_p2l(L.red, stp)) {
+        } else if (p2l && !solve_p2l(L.red, stp)) {
           status |= DPGICP_STOP_DEGENERATE;            /* geometry does not constrain the pose */
           st = 2;
         } else {
           const double invK = __ddiv_rn(1.0, (double)K);
-          if (P.metric != DPGICP_METRIC_POINT_TO_LINE) solve_p2p(L.red, invK, stp);
+          if (!p2l) solve_p2p(L.red, invK, stp);
           const float sc = stp[0], ss = stp[1], stx = stp[2], sty = stp[3];
           L.step[0] = sc; L.step[1] = ss; L.step[2] = stx; L.step[3] = sty;
           /* final = step * final (App. A.3-6) */
@@ -1363,7 +1373,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           const float ntx = __fadd_rn(__fadd_rn(__fmul_rn(sc, ftx), __fmul_rn(-ss, fty)), stx);
           const float nty = __fadd_rn(__fadd_rn(__fmul_rn(ss, ftx), __fmul_rn(sc, fty)), sty);
           fc = nc; fs = nsn; ftx = ntx; fty = nty;
-          if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) { L.fin[0] = fc; L.fin[1] = fs; L.fin[2] = ftx; L.fin[3] = fty; }
+          if constexpr (search_is_projective(SEARCH)) { L.fin[0] = fc; L.fin[1] = fs; L.fin[2] = ftx; L.fin[3] = fty; }
           ++iterations;
           mse = __dmul_rn(__dmul_rn((double)L.red[9], 1.0 / kScaleD2), invK);
           /* DefaultConvergenceCriteria (App. A.5), in PCL's order */
@@ -1411,7 +1421,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           const int k = t * kTile + lane;
           float2 p = ld_pt(L.src, k);
           if (k < ns) { p = xform(sc, ss, stx, sty, p); st_pt(L.src, k, p); }
-          if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
+          if constexpr (!search_is_projective(SEARCH)) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
         }
       }
       if (tid == 0 && crank == 0) ++c_iters;
@@ -1419,7 +1429,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
       __syncthreads();
       PH_MARK(5);                                     /* wait */
       if (stop) break;
-      if constexpr (SEARCH == DPGICP_SEARCH_PRUNED) {
+      if constexpr (search_is_pruned(SEARCH) && !search_is_flat(SEARCH)) {
         build_super_boxes(L.sbox, gs, L.ssup, warp, nw, lane);
         __syncthreads();
       }
@@ -1479,10 +1489,10 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
           float2 p = make_float2(kPad, kPad);
           if (k < ns) { p = xform(Tc, Ts, Ttx, Tty, __ldg(srow + (size_t)k * div)); }
           st_pt(L.src, k, p);
-          if constexpr (SEARCH != DPGICP_SEARCH_PROJECTIVE) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
+          if constexpr (!search_is_projective(SEARCH)) store_tile_boxes(p, k < ns, t, L.sbox, L.stile, lane);
         }
         __syncthreads();
-        if constexpr (SEARCH == DPGICP_SEARCH_PRUNED) {
+        if constexpr (search_is_pruned(SEARCH) && !search_is_flat(SEARCH)) {
           build_super_boxes(L.sbox, gs, L.ssup, warp, nw, lane);
           __syncthreads();
         }
@@ -1594,7 +1604,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(
   if (lane == 0) {
     atomicAdd(P.counters + 2, (unsigned long long)stats.scans * (kGroup * 32ull));
   }
-  if constexpr (SEARCH == DPGICP_SEARCH_PROJECTIVE) {
+  if constexpr (search_is_projective(SEARCH)) {
     const unsigned we = __reduce_add_sync(0xffffffffu, stats.window_evals);   /* per-lane counts, may wrap past 2^32 per warp: an executed-work statistic only */
     if (lane == 0) atomicAdd(P.counters + 2, (unsigned long long)we);
   }
