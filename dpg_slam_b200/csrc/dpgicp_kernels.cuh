@@ -1066,14 +1066,20 @@ __device__ __forceinline__ float select_tau(const SmemLayout &L, int n_pad, int 
 #ifndef DPGICP_TARGET_WARPS
 #define DPGICP_TARGET_WARPS 28
 #endif
-/* CTAs of up to 4 warps.  32 (8 x 4 warps per SM, 64 registers, fits since the reduction scratch is sized by the CTA
- * width) was measured equal to 28 (7 x 4 warps, 72 registers) within 0.5 %: the stage is held back by issue slots,
- * shared-memory write-back and the FP32 pipe together, not by latency that more resident warps could hide. */
+/* CTAs of up to 4 warps: 28 resident warps per SM (7 x 4 warps, 72 registers) for the general instantiations, 32 (8 x 4
+ * warps, 64 registers; fits since the reduction scratch is sized by the CTA width) for the stock-configuration ones.
+ * Measured: with the general kernel the 64-register build spills in the pass loop and 8 CTAs equal 7 (471.6 k vs 474.4 k
+ * pairs/s); the stock kernel, with the point-to-line / rejector / hook code compiled out, spills less and gains
+ * (486 k -> 497 k pairs/s corridor, 692 k -> 711 k loop closure). */
 #ifndef DPGICP_TARGET_WARPS_NARROW
 #define DPGICP_TARGET_WARPS_NARROW 28
 #endif
-__host__ __device__ constexpr int min_ctas(int warps) {
-  const int target = warps <= 4 ? DPGICP_TARGET_WARPS_NARROW : DPGICP_TARGET_WARPS;
+#ifndef DPGICP_TARGET_WARPS_NARROW_STOCK
+#define DPGICP_TARGET_WARPS_NARROW_STOCK 32
+#endif
+__host__ __device__ constexpr int min_ctas(int warps, int search) {
+  const int target = warps <= 4 ? (search_is_stock(search) ? DPGICP_TARGET_WARPS_NARROW_STOCK : DPGICP_TARGET_WARPS_NARROW)
+                                : DPGICP_TARGET_WARPS;
   return (target / warps) < 1 ? 1 : (target / warps) > 16 ? 16 : (target / warps);   /* 16, 17, 32 -> 1 */
 }
 
@@ -1096,7 +1102,7 @@ __device__ __forceinline__ T *peer_smem(T *p, int rank) {
 }
 
 template <int WARPS, int SEARCH, int CSIZE>
-__global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS)) icp_pairs_kernel(const KernelParams P) {
+__global__ void __launch_bounds__(WARPS * 32, min_ctas(WARPS, SEARCH)) icp_pairs_kernel(const KernelParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout L = carve(smem_raw, P.n_cap, search_is_projective(SEARCH), (int)(blockDim.x >> 5));
   int tid = threadIdx.x;
