@@ -56,7 +56,18 @@ def transform(T: np.ndarray, pts3: np.ndarray) -> np.ndarray:
     return (pts3.astype(F) @ R.T + t).astype(F)
 
 
-def umeyama_float32(src3: np.ndarray, dst3: np.ndarray) -> np.ndarray:
+def _svd3(sigma: np.ndarray, engine: str):
+    """float32 SVD of the 3x3 covariance: LAPACK (numpy) or OpenCV's Jacobi SVD — a one-sided Jacobi iteration in float32,
+    the family Eigen's JacobiSVD (what PCL runs) belongs to.  Two engines, so that the report can say how much of the
+    stop-iteration noise is the SVD implementation's."""
+    if engine == "opencv":
+        import cv2
+        w, u, vt = cv2.SVDecomp(np.ascontiguousarray(sigma, F))
+        return u.astype(F), w.ravel().astype(F), vt.astype(F)
+    return np.linalg.svd(sigma.astype(F))
+
+
+def umeyama_float32(src3: np.ndarray, dst3: np.ndarray, svd: str = "lapack") -> np.ndarray:
     """Eigen::umeyama(src, dst, with_scaling = false) in float32, as TransformationEstimationSVD<.., float> calls it
     (App. A.3-5): means, covariance (1/n) sum (dst - mu_d)(src - mu_s)^T, SVD, R = U diag(1, 1, +-1) V^T."""
     n = F(src3.shape[0])
@@ -64,7 +75,7 @@ def umeyama_float32(src3: np.ndarray, dst3: np.ndarray) -> np.ndarray:
     mu_d = (dst3.sum(axis=0, dtype=F) / n).astype(F)
     sd, dd = (src3 - mu_s).astype(F), (dst3 - mu_d).astype(F)
     sigma = ((dd.T @ sd) * (F(1.0) / n)).astype(F)
-    U, _, Vt = np.linalg.svd(sigma.astype(F))
+    U, _, Vt = _svd3(sigma, svd)
     S = np.ones(3, F)
     if np.linalg.det(U.astype(np.float64)) * np.linalg.det(Vt.astype(np.float64)) < 0:
         S[2] = F(-1.0)
@@ -75,10 +86,11 @@ def umeyama_float32(src3: np.ndarray, dst3: np.ndarray) -> np.ndarray:
     return T
 
 
-def icp(src_xy, tgt_xy, guess, max_iterations=500, eps=5e-9, max_dist=0.6, reciprocal=True, trace=None, nn="scipy"):
+def icp(src_xy, tgt_xy, guess, max_iterations=500, eps=5e-9, max_dist=0.6, reciprocal=True, trace=None, nn="scipy", svd="lapack"):
     """-> dict(T (4x4 float32), converged, iterations, stop, n_corr, mse).  stop in {"iterations", "transform",
     "abs_mse", "no_correspondences"}.  ``trace`` (a list) receives (final BEFORE the pass as (c, s, tx, ty), K) per pass.
-    ``nn``: "scipy" (cKDTree) or "flann" (OpenCV's FLANN single kd-tree: PCL's own neighbour library)."""
+    ``nn``: "scipy" (cKDTree) or "flann" (OpenCV's FLANN single kd-tree: PCL's own neighbour library); ``svd``: "lapack" or
+    "opencv" (a float32 Jacobi SVD)."""
     Tree = FlannTree if nn == "flann" else ScipyTree
     src = np.zeros((len(src_xy), 3), F)
     tgt = np.zeros((len(tgt_xy), 3), F)
@@ -114,7 +126,7 @@ def icp(src_xy, tgt_xy, guess, max_iterations=500, eps=5e-9, max_dist=0.6, recip
         if K < 3:                                                       # A.3-4
             out.update(converged=False, stop="no_correspondences", iterations=it, T=final)
             return out
-        step = umeyama_float32(cur[idx], tgt[j[idx]])                   # A.3-5
+        step = umeyama_float32(cur[idx], tgt[j[idx]], svd)              # A.3-5
         cur = transform(step, cur)                                      # A.3-6
         final = (step @ final).astype(F)
         it += 1

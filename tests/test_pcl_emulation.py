@@ -30,7 +30,7 @@ def _angle_of(T4):
     return float(np.arctan2(np.float64(T4[1]), np.float64(T4[0])))
 
 
-def compare_pairs(wl, divisor, n_sample):
+def compare_pairs(wl, divisor, n_sample, nn="scipy", svd="lapack"):
     """-> list of dict rows, one per sampled pair"""
     pts, off = O.clouds_from_ranges(wl.ranges, wl.scanner)
     p = Params.defaults(downsample_divisor=divisor)
@@ -40,7 +40,7 @@ def compare_pairs(wl, divisor, n_sample):
         S, T = pts[off[s]:off[s + 1]][::divisor], pts[off[t]:off[t + 1]][::divisor]
         res, T_iter, n_corr = O.icp(S, T, wl.guess[k], p, fast=1, trace=True)
         tr = []
-        emu = E.icp(S, T, wl.guess[k], trace=tr)
+        emu = E.icp(S, T, wl.guess[k], trace=tr, nn=nn, svd=svd)
         ex, ey, eth = E.pose_of(emu["T"])
         common = min(len(tr), len(T_iter))
         dt = dth = 0.0
@@ -69,7 +69,8 @@ def summarize(rows):
                 max_d_final_rad_flipped=max((r["d_final_rad"] for r in flip), default=0.0),
                 max_d_pass_m=max(r["d_pass_m"] for r in rows), max_d_pass_rad=max(r["d_pass_rad"] for r in rows),
                 passes_compared=passes, passes_with_equal_K=sum(r["k_pass_equal"] for r in rows),
-                it_oracle_mean=float(np.mean([r["it_oracle"] for r in rows])), it_emu_mean=float(np.mean([r["it_emu"] for r in rows])))
+                it_oracle_mean=float(np.mean([r["it_oracle"] for r in rows])), it_emu_mean=float(np.mean([r["it_emu"] for r in rows])),
+                stop_iteration_abs_diff_p50_p90_max=[float(x) for x in np.percentile([abs(r["it_oracle"] - r["it_emu"]) for r in rows], [50, 90, 100])])
 
 
 CASES = [

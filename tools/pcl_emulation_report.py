@@ -20,8 +20,15 @@ cases = [
 ]
 out = {"what": "oracle (oracle/dpg_oracle.c) vs independent whole-loop PCL emulation (tests/pcl_emulation.py); PCL itself is absent",
        "cases": []}
-for name, wl, div, n in cases:
-    rows = T.compare_pairs(wl, div, n)
+engines = [("scipy", "lapack")]
+try:
+    import cv2  # noqa: F401
+    engines.append(("flann", "opencv"))       # PCL's own neighbour library + a float32 Jacobi SVD (Eigen's family)
+except ImportError:
+    pass
+for (name0, wl, div, n), (nn, svd) in [(c, e) for c in cases for e in engines]:
+    name = f"{name0} [nn={nn}, svd={svd}]"
+    rows = T.compare_pairs(wl, div, n, nn=nn, svd=svd)
     s = T.summarize(rows)
     s["name"] = name
     s["iterations_oracle_hist"] = np.percentile([r["it_oracle"] for r in rows], [50, 90, 99, 100]).tolist()
