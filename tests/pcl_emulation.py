@@ -56,10 +56,97 @@ def transform(T: np.ndarray, pts3: np.ndarray) -> np.ndarray:
     return (pts3.astype(F) @ R.T + t).astype(F)
 
 
+def _jacobi_svd_eigen_style(a: np.ndarray):
+    """Two-sided Jacobi SVD of a square float32 matrix, every operation in float32: the algorithm of Eigen 3.3's
+    JacobiSVD (what PCL's TransformationEstimationSVD runs through Eigen::umeyama) — scale by the largest entry, sweep over
+    the (p, q) pairs while an off-diagonal entry exceeds 2 eps x the largest diagonal entry, each 2x2 block first made
+    symmetric by a left rotation, then diagonalised by a Jacobi rotation; singular values made positive by flipping columns
+    of U, then sorted.  RESTATED FROM THE PUBLISHED ALGORITHM (Eigen is absent from this image): it cannot be checked
+    against Eigen here; it is a third, independent float32 SVD for the report, of the same family."""
+    n = a.shape[0]
+    tiny = F(np.finfo(np.float32).tiny)
+    precision = F(2.0) * F(np.finfo(np.float32).eps)
+    scale = F(np.abs(a).max())
+    if scale == 0:
+        scale = F(1.0)
+    W = (a.astype(F) / scale).astype(F)
+    U, V = np.eye(n, dtype=F), np.eye(n, dtype=F)
+
+    def rot_left(M, p, q, c, s):          # rows p, q of M <- J [row p; row q], J = [c s; -s c]
+        x, y = M[p, :].copy(), M[q, :].copy()
+        M[p, :] = (c * x + s * y).astype(F)
+        M[q, :] = (-s * x + c * y).astype(F)
+
+    def rot_right(M, p, q, c, s):         # cols p, q of M <- [col p, col q] J, J = [c s; -s c]
+        x, y = M[:, p].copy(), M[:, q].copy()
+        M[:, p] = (c * x - s * y).astype(F)
+        M[:, q] = (s * x + c * y).astype(F)
+
+    def make_jacobi(x, y, z):             # J with J^T [x y; y z] J diagonal
+        deno = F(2.0) * abs(y)
+        if deno < tiny:
+            return F(1.0), F(0.0)
+        tau = F((x - z) / deno)
+        w = F(np.sqrt(F(tau * tau) + F(1.0)))
+        t = F(1.0) / F(tau + w) if tau > 0 else F(1.0) / F(tau - w)
+        sign_t = F(1.0) if t > 0 else F(-1.0)
+        nrm = F(1.0) / F(np.sqrt(F(t * t) + F(1.0)))
+        return nrm, F(-sign_t * F(y / abs(y)) * abs(t) * nrm)
+
+    max_diag = F(np.abs(np.diag(W)).max())
+    for _sweep in range(60):
+        finished = True
+        for p in range(1, n):
+            for q in range(p):
+                thr = max(tiny, F(precision * max_diag))
+                if abs(W[p, q]) > thr or abs(W[q, p]) > thr:
+                    finished = False
+                    m00, m01, m10, m11 = W[p, p], W[p, q], W[q, p], W[q, q]
+                    t, d = F(m00 + m11), F(m10 - m01)
+                    if abs(d) < tiny:
+                        c1, s1 = F(1.0), F(0.0)
+                    else:
+                        u = F(t / d)
+                        tmp = F(np.sqrt(F(1.0) + F(u * u)))
+                        s1, c1 = F(F(1.0) / tmp), F(u / tmp)
+                    # the 2x2 block after the symmetrising rotation
+                    b00, b01 = F(c1 * m00 + s1 * m10), F(c1 * m01 + s1 * m11)
+                    b11 = F(-s1 * m01 + c1 * m11)
+                    cr, sr = make_jacobi(b00, b01, b11)
+                    # j_left = rot1 * j_right^T
+                    cl = F(c1 * cr - s1 * (-sr))
+                    sl = F(c1 * (-sr) + s1 * cr)
+                    rot_left(W, p, q, cl, sl)
+                    rot_right(U, p, q, cl, -sl)               # U <- U * j_left^T
+                    rot_right(W, p, q, cr, sr)
+                    rot_right(V, p, q, cr, sr)
+                    max_diag = max(max_diag, F(max(abs(W[p, p]), abs(W[q, q]))))
+        if finished:
+            break
+    sv = np.zeros(n, F)
+    for i in range(n):
+        aii = W[i, i]
+        sv[i] = abs(aii)
+        if aii < 0:
+            U[:, i] = -U[:, i]
+    sv = (sv * scale).astype(F)
+    for i in range(n):                                        # selection sort, as Eigen: largest first, swap columns
+        k = int(np.argmax(sv[i:])) + i
+        if sv[k] == 0:
+            break
+        if k != i:
+            sv[[i, k]] = sv[[k, i]]
+            U[:, [i, k]] = U[:, [k, i]]
+            V[:, [i, k]] = V[:, [k, i]]
+    return U, sv, V.T.copy()
+
+
 def _svd3(sigma: np.ndarray, engine: str):
     """float32 SVD of the 3x3 covariance: LAPACK (numpy) or OpenCV's Jacobi SVD — a one-sided Jacobi iteration in float32,
     the family Eigen's JacobiSVD (what PCL runs) belongs to.  Two engines, so that the report can say how much of the
     stop-iteration noise is the SVD implementation's."""
+    if engine == "eigen_jacobi":
+        return _jacobi_svd_eigen_style(np.asarray(sigma, F))
     if engine == "opencv":
         import cv2
         w, u, vt = cv2.SVDecomp(np.ascontiguousarray(sigma, F))

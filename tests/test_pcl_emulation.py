@@ -190,3 +190,40 @@ def test_flann_on_exact_ties_same_distance_other_index():
     # the differing picks are minimisers too: same distance from the query, bit for bit
     alt = ((src[differ] - tgt[jf[differ]]) ** 2).astype(np.float32)
     assert np.array_equal((alt[:, 0] + alt[:, 1]).astype(np.float32).view(np.uint32), want_d2[differ].view(np.uint32))
+
+
+def test_eigen_style_jacobi_svd_is_a_valid_float32_svd():
+    """The restated two-sided Jacobi SVD (the algorithm of Eigen's JacobiSVD, tests/pcl_emulation.py) on random and on
+    planar (rank 2, like the ICP covariance of z = 0 points) 3x3 matrices: U diag(s) V^T reproduces the matrix to float32
+    accuracy, U and V are orthogonal, the singular values are sorted and equal LAPACK's in double to 2e-5 relative."""
+    rng = np.random.default_rng(1)
+    for k in range(200):
+        a = rng.normal(size=(3, 3)).astype(np.float32)
+        if k % 3 == 0:
+            a[:, 2] = 0
+            a[2, :] = 0
+        U, s, Vt = E._jacobi_svd_eigen_style(a)
+        assert np.abs(U @ np.diag(s) @ Vt - a).max() <= 4e-6 * max(np.abs(a).max(), 1.0)
+        assert np.abs(U.T @ U - np.eye(3)).max() <= 2e-6 and np.abs(Vt @ Vt.T - np.eye(3)).max() <= 2e-6
+        assert np.all(np.diff(s) <= 0) and np.all(s >= 0)
+        assert np.allclose(s, np.linalg.svd(a.astype(np.float64), compute_uv=False), rtol=2e-5, atol=2e-6)
+
+
+def test_oracle_loop_against_emulation_on_flann_and_eigen_style_jacobi():
+    """The emulation closest to what PCL links — FLANN neighbours, an Eigen-style float32 two-sided Jacobi SVD — against the
+    oracle on divisor-5 corridor pairs (the reference's default).  Like the LAPACK engine, and unlike OpenCV's SVD (which
+    accumulates in double), this float32-pure SVD leaves the rotation's diagonal an ulp off 1.0f on part of the pairs, so
+    PCL's rotation criterion `cos >= 1 - 5e-9` keeps failing and those pairs creep on to |d mse| < 1e-12 or the iteration
+    limit, while the oracle's closed-form step stops on the transformation criterion: the stop ITERATION of PCL's loop is
+    decided by the last ulp of its SVD.  What holds for every engine: hasConverged() agrees, the iterates agree pass by
+    pass while both run, pairs that stop at the same iteration end within 1e-4 m / 2e-5 rad, the others within the creep
+    of the sub-threshold steps."""
+    pytest.importorskip("cv2")
+    rows = compare_pairs(synth.config_corridor(n_pairs=60, seed=2), 5, 30, nn="flann", svd="eigen_jacobi")
+    s = summarize(rows)
+    print(f"\n[pcl emulation, flann + eigen-style jacobi] {s}")
+    assert all(r["conv_equal"] for r in rows)
+    assert s["max_d_pass_m"] <= 5e-3 and s["max_d_pass_rad"] <= 1e-3, s
+    assert s["same_stop_iteration"] >= 0.5 * s["pairs"], s
+    assert s["max_d_final_m_same_stop"] <= 1e-4 and s["max_d_final_rad_same_stop"] <= 2e-5, s
+    assert s["max_d_final_m_flipped"] <= 1e-3 and s["max_d_final_rad_flipped"] <= 1e-4, s

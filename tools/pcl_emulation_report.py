@@ -24,6 +24,7 @@ engines = [("scipy", "lapack")]
 try:
     import cv2  # noqa: F401
     engines.append(("flann", "opencv"))       # PCL's own neighbour library + a float32 Jacobi SVD (Eigen's family)
+    engines.append(("flann", "eigen_jacobi")) # ... + Eigen 3.3's two-sided Jacobi algorithm restated in float32
 except ImportError:
     pass
 for (name0, wl, div, n), (nn, svd) in [(c, e) for c in cases for e in engines]:
