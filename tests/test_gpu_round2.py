@@ -429,3 +429,24 @@ def test_small_batches_start_at_the_stage_that_keeps_them(gpu_matcher):
         assert gpu_matcher.last_run_counters()["kernel_launches"] - before == 1
         assert few.tobytes() == big[:20].tobytes()
         assert n_big >= 1
+
+
+def test_cuda_correspondences_equal_flann_golden_vectors(gpu_matcher):
+    """The committed FLANN golden vectors (tests/golden/flann_nn.json, generated by tools/make_flann_golden.py from OpenCV's
+    bundled FLANN) against dpgicp_correspondences: forward neighbours, binary32 squared distances and reciprocal sets."""
+    import json
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "flann_nn.json")))["cases"]
+
+    def hexf(h, cols=None):
+        a = np.array([int(x, 16) for x in h], np.uint32).view(np.float32)
+        return a.reshape(-1, cols) if cols else a
+
+    for c in cases:
+        S, T, Tm = hexf(c["source_hex"], 2), hexf(c["target_hex"], 2), hexf(c["T_hex"])
+        jf = np.array(c["flann_forward_index"]); d2f = hexf(c["flann_forward_d2_hex"]); back = np.array(c["flann_backward_index"])
+        inside = d2f.astype(np.float64) <= 0.36
+        got, got_d2 = gpu_matcher.correspondences(S, T, Tm, Params.defaults(use_reciprocal=0))
+        assert np.array_equal(got >= 0, inside) and np.array_equal(got[inside], jf[inside]), (c["workload"], c["pair"], c["iterate"])
+        assert np.array_equal(got_d2[inside].view(np.uint32), d2f[inside].view(np.uint32))
+        got_r, _ = gpu_matcher.correspondences(S, T, Tm, Params.defaults(use_reciprocal=1))
+        assert np.array_equal(got_r, np.where(inside & (back == np.arange(len(S))), jf, -1))

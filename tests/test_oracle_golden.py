@@ -519,3 +519,36 @@ def test_enumerate_online_is_the_reference_loop():
                     if d <= (5.0 if ps[i] == ps[pre] else 2.0):
                         want.append((pre, i))
         assert list(zip(src.tolist(), tgt.tolist())) == want, n
+
+
+# ---- neighbour search: golden vectors from a real FLANN kd-tree (tools/make_flann_golden.py) ---------------------------
+def _flann_cases():
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flann_nn.json")
+    return json.load(open(path))["cases"]
+
+
+def _hex_f32(h, cols=None):
+    a = np.array([int(x, 16) for x in h], np.uint32).view(np.float32)
+    return a.reshape(-1, cols) if cols else a
+
+
+def test_oracle_correspondences_equal_flann_golden_vectors():
+    """tests/golden/flann_nn.json holds what a real FLANN single kd-tree (the library PCL's KdTreeFLANN wraps, exact search)
+    returned for the forward and backward neighbour queries of PCL's reciprocal correspondence estimation at 18 iterates of
+    config-2 / config-3 pairs.  The oracle's forward neighbours and squared distances (bit for bit) and its reciprocal sets
+    against them — no OpenCV needed to run this."""
+    n_q = 0
+    for c in _flann_cases():
+        S, T, Tm = _hex_f32(c["source_hex"], 2), _hex_f32(c["target_hex"], 2), _hex_f32(c["T_hex"])
+        jf = np.array(c["flann_forward_index"]); d2f = _hex_f32(c["flann_forward_d2_hex"]); back = np.array(c["flann_backward_index"])
+        cur = O.transform_points(Tm, S)
+        inside = d2f.astype(np.float64) <= 0.36
+        _, fwd, fwd_d2 = O.correspondences(cur, T, Params.defaults(use_reciprocal=0))
+        assert np.array_equal(fwd >= 0, inside), (c["workload"], c["pair"], c["iterate"])
+        assert np.array_equal(fwd[inside], jf[inside])
+        assert np.array_equal(fwd_d2[inside].view(np.uint32), d2f[inside].view(np.uint32))
+        _, rec, _ = O.correspondences(cur, T, Params.defaults(use_reciprocal=1))
+        assert np.array_equal(rec, np.where(inside & (back == np.arange(len(cur))), jf, -1))
+        n_q += int(inside.sum())
+    assert n_q > 2500
