@@ -494,7 +494,9 @@ __device__ __forceinline__ float below(float d2) {
  * box contains its groups' boxes and every operation of the lower bound is monotone, so its bound never exceeds
  * theirs: nothing a flat pass would have kept is dropped.  Groups still come in ascending order.  The brute-force
  * variant walks all groups, 32 per round.  FLAT (kSearchPrunedFlat): a cloud of at most 32 groups is tested in one flat
- * round and needs no upper level.  Defines mask (bit b = group (b < 16 ? g0 : g1) + (b & 15)). */
+ * round and needs no upper level.  There is no branch around a test: a lane past the last box reads whatever follows the
+ * array in this CTA's shared memory (at most 31 slots of 16 bytes further — the next box array, the reduction scratch —
+ * always inside the allocation) and is masked out of the ballot.  Defines mask (bit b = group (b < 16 ? g0 : g1) + (b & 15)). */
 #define DPG_ROUNDS_BEGIN(QBOX, BMAX)                                                                                     \
   int base__ = 0;                                                                                                        \
   unsigned up__ = 0u;                                                                                                    \
